@@ -1,0 +1,134 @@
+"""CPU: the oracle restatement (oracle/) pinned against fixtures produced by the unmodified
+reference (tests/golden/, made by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import guide_oracle as go, guide_params, sampler_oracle as so, scenes, unet_oracle, weights
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return weights.seeded_state_dict(0)
+
+
+def test_state_dict_layout():
+    table = weights.key_table()
+    assert len(table) == 290
+    assert sum(int(np.prod(s)) for _, s, _ in table) == 29938471
+
+
+def test_unet_oracle_matches_reference(golden, sd):
+    g = golden("unet_forward.npz")
+    x = torch.tensor(g["x"])
+    for t in (255, 128, 1):
+        taps = {}
+        with torch.no_grad():
+            eps = unet_oracle.unet_forward(sd, x, t, taps).numpy()
+        np.testing.assert_allclose(eps, g["eps_t%d" % t], rtol=0, atol=1e-6)
+        if t == 128:
+            for key in g.files:
+                if key.startswith("tap_t128/"):
+                    ref = g[key]
+                    mine = taps[key.split("/", 1)[1]].numpy()
+                    np.testing.assert_allclose(mine, ref[:, :, :mine.shape[2]], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("case", ["mixed", "iv", "sv_axis"])
+def test_guide_oracle_matches_reference(golden, case):
+    g = golden("guide.npz")
+    guides, bpg = [int(v) for v in g[case + "/guides"]], int(g[case + "/bpg"])
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], bpg)
+    scene, q, ld = g[case + "/scene"], g[case + "/q"], g["link_dims"]
+    np.testing.assert_allclose(ld, go.LINK_DIMS, rtol=0, atol=1e-7)
+    B = q.shape[0]
+    for t in (254, 100, 6):
+        ref = g["%s/grad_t%d" % (case, t)]
+        scale = max(1.0, np.abs(ref).max())
+        a = go.gradient_autograd(q, scenes.START, scenes.GOAL, scene, cfgs, t)
+        b = go.gradient_analytic(q, scenes.START, scenes.GOAL, scene, cfgs, t)
+        assert np.abs(a - ref).max() <= 2e-6 * scale
+        assert np.abs(b - ref).max() <= 2e-6 * scale
+    omin, omax = go.obstacle_aabbs(scene, cfgs["expansion"][:, 99], cfgs["clearance"][:, 99], rows=B)
+    qt = torch.tensor(q, dtype=torch.float32)
+    np.testing.assert_allclose(go.iv_cost(qt, omin, omax).numpy(), g[case + "/iv_t100"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(go.sv_cost(qt, scenes.START, scenes.GOAL, omin, omax).numpy(),
+                               g[case + "/sv_t100"], rtol=0, atol=1e-7)
+    omin0, omax0 = go.obstacle_aabbs(scene, rows=B)
+    np.testing.assert_allclose(go.iv_cost(qt[:, :, :1], omin0, omax0).numpy(), g[case + "/cost_t0"],
+                               rtol=0, atol=1e-7)
+    traj = np.concatenate([np.broadcast_to(scenes.START[None, :, None], (B, 7, 1)), q,
+                           np.broadcast_to(scenes.GOAL[None, :, None], (B, 7, 1))], axis=2)
+    fs = go.final_sv_costs(traj, scenes.START, scenes.GOAL, scene)
+    np.testing.assert_allclose(fs, g[case + "/final_sv"], rtol=1e-5, atol=1e-7)
+    assert int(np.argmin(fs)) == int(g[case + "/best_index"])
+
+
+def test_guide_nan_poisoning(golden):
+    g = golden("guide.npz")
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in (1, 9)], 1)
+    for fn in (go.gradient_autograd, go.gradient_analytic):
+        out = fn(g["nan/q"], scenes.START, scenes.GOAL, g["nan/scene"], cfgs, 100)
+        assert np.isnan(out).all() and np.isnan(g["nan/grad_t100"]).all()
+
+
+def test_schedule_and_tables():
+    beta, alpha, abar = so.schedule()
+    assert beta.shape == (255,) and abs(beta[0] - 0.02 / 255) < 1e-15 and abs(beta[-1] - 0.02) < 1e-15
+    assert abs(abar[-1] - np.prod(1 - beta)) < 1e-15
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in (18, 1)], 2)
+    # guide18: isr2 [10,40) then isr3 [0,20) overwrites 10..19 with zeros
+    assert cfgs["expansion"][0, 15] == 0.0 and cfgs["expansion"][0, 25] > 0.0
+    assert cfgs["expansion"][0, 100] == 0.4 and cfgs["expansion"][2, 100] == 0.0
+    assert cfgs["guidance_schedule"][0, 7] == 0.05 and abs(cfgs["guidance_schedule"][2, 254] - (1.4 + 254 / 255)) < 1e-12
+
+
+def _replay(name):
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "sampler_%s.npz" % name))
+    guides, bpg = [int(v) for v in g["guides"]], int(g["bpg"])
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], bpg)
+    B = cfgs["total_batch_size"]
+    rng = np.random.default_rng(int(g["noise_seed"]))
+    noise = [rng.normal(size=(B, 7, 50)) for _ in range(255)]
+    assert abs(sum(n.sum() for n in noise) - float(g["noise_checksum"])) < 1e-9
+    return g, cfgs, noise
+
+
+@pytest.fixture(scope="module")
+def sd02():
+    return weights.seeded_state_dict(0, final_gain=0.2)
+
+
+def test_sampler_oracle_teacher_forced(golden, sd02):
+    """Single steps from the reference's own recorded states: posterior, guide, update."""
+    sd = sd02
+    g, cfgs, noise = _replay("mixed")
+    beta, alpha, abar = so.schedule()
+    for t in [int(s) for s in g["steps"]]:
+        x = g["x_in_t%d" % t]
+        with torch.no_grad():
+            eps = unet_oracle.unet_forward(sd, torch.tensor(x, dtype=torch.float32), t).numpy()
+        np.testing.assert_allclose(eps, g["eps_t%d" % t], rtol=0, atol=2e-6)
+        xp = so.posterior_step(x, t, g["eps_t%d" % t], noise[255 - t], beta, alpha, abar)
+        np.testing.assert_allclose(xp, g["x_post_t%d" % t], rtol=0, atol=1e-12)
+        if t % 2 == 0 and t >= 5:
+            G = go.gradient_analytic(so.clip_joints(xp[:, :, 1:-1]), scenes.START, scenes.GOAL,
+                                     g["scene"], cfgs, t)
+            ref = g["grad_t%d" % t]
+            assert np.abs(G - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+            xp[:, :, 1:-1] -= cfgs["guidance_schedule"][:, t - 1, None, None] * ref
+        xp[:, :, 0], xp[:, :, -1] = scenes.START, scenes.GOAL
+        np.testing.assert_allclose(xp, g["x_out_t%d" % t], rtol=0, atol=1e-12)
+
+
+def test_sampler_oracle_end_to_end_iv(golden, sd02):
+    """Full 255 steps, iv guides [1,2,3] (BASELINE config 3 ensemble): <= 1e-4 rad."""
+    sd = sd02
+    g, cfgs, noise = _replay("iv")
+    out = so.denoise_guided(sd, g["scene"], cfgs, scenes.START, scenes.GOAL, g["x_T"], noise,
+                            gradient="analytic")
+    assert np.abs(out - g["final"]).max() <= 1e-4
+    best = go.choose_best_trajectory(out, scenes.START, scenes.GOAL, g["scene"])
+    assert np.abs(best - g["best"]).max() <= 1e-4
