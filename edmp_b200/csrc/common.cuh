@@ -1,0 +1,44 @@
+// Shared helpers for the edmp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace edmp {
+
+void set_error(const std::string& msg);
+
+#define EDMP_CK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::edmp::set_error(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" +  \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ")");                   \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+#define EDMP_REQUIRE(cond, msg)                                              \
+  do {                                                                       \
+    if (!(cond)) {                                                           \
+      ::edmp::set_error(std::string("edmp: ") + (msg) + " [" #cond "]");     \
+      return 2;                                                              \
+    }                                                                        \
+  } while (0)
+
+constexpr int kHorizon = 50;
+constexpr int kDof = 7;
+constexpr int kRowElems = kHorizon * kDof;  // 350
+constexpr int kTSteps = 255;
+constexpr int kMaxObs = 64;
+
+// x * tanh(softplus(x)) (reference blocks.py:27 nn.Mish), via tanh(log1p(e^x)) = n/(n+2), n = e^x(e^x+2).
+__device__ __forceinline__ float mish_f(float x) {
+  if (x > 20.0f) return x;
+  float e = expf(x);
+  float n = e * (e + 2.0f);
+  return x * (n / (n + 2.0f));
+}
+
+}  // namespace edmp

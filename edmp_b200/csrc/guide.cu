@@ -1,0 +1,626 @@
+// AABB intersection-volume / swept-volume guide: cost and closed-form gradient kernels.
+//
+// Replaces reference lib/guide.py: forward_kinematics :74-98 (modified-DH chain), link boxes
+// :243-375, define_obstacles :118-158, cost :354-395, swept_volume_cost :473-537, get_gradient
+// :597-635 (autograd there, analytic here -- SURVEY.md section 8 a-G), choose_best_trajectory
+// :637-653.  One CTA per trajectory row, one thread per waypoint (or segment); the scene's
+// obstacle boxes are staged once per CTA into shared memory.
+#include "common.cuh"
+#include "guide.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace edmp {
+
+// ---- constant geometry ---------------------------------------------------------------------
+// modified-DH rows (a, d, cos(alpha), sin(alpha)) evaluated in float32 like the reference does
+// (lib/guide.py:29-38 + get_tf_mat :45-72; cos(float32(pi/2)) is -4.37e-8, not 0).
+__constant__ float c_dh[7][4];
+// link-box centre frames relative to the driving joint frame, 3x4 row major (lib/guide.py:289-340)
+__constant__ float c_frame[9][12];
+__constant__ double c_joint_lo[7];
+__constant__ double c_joint_hi[7];
+
+static const double kDhHost[7][3] = {  // a, d, alpha
+    {0, 0.333, 0},          {0, 0, -M_PI / 2},    {0, 0.316, M_PI / 2}, {0.0825, 0, M_PI / 2},
+    {-0.0825, 0.384, -M_PI / 2}, {0, 0, M_PI / 2}, {0.088, 0, M_PI / 2}};
+static const double kFrameT[9][3] = {{8.71e-05, -3.709035e-02, -6.851545e-02},
+                                     {-8.425e-05, -6.93950016e-02, 3.71961970e-02},
+                                     {0.0414576, 0.0281429, -0.03293086},
+                                     {-4.12337575e-02, 3.44296512e-02, 2.79226985e-02},
+                                     {3.3450000e-05, 3.7388050e-02, -1.0619285e-01},
+                                     {4.21935000e-02, 1.52195003e-02, 6.07699933e-03},
+                                     {1.86357500e-02, 1.85788569e-02, 7.94137484e-02},
+                                     {-1.26717073e-03, -1.25294673e-03, 1.27018693e-01},
+                                     {9.29352476e-03, 9.28272434e-03, 1.92390375e-01}};
+// Built-in link box extents: AABBs of robofin's hd_meshes/collision/{link1..7,hand,finger}.obj
+// (finger y x4, lib/guide.py:278-279) -- stand-in for pybullet_data's meshes, SURVEY.md 8c.
+static const double kLinkDims[9][3] = {
+    {0.110016, 0.184406, 0.247002}, {0.110033, 0.249024, 0.184393}, {0.192511, 0.166063, 0.176002},
+    {0.192507, 0.179, 0.166053},    {0.109996, 0.18493, 0.311199},  {0.179925, 0.132863, 0.100244},
+    {0.125333, 0.125297, 0.0548},   {0.063045, 0.204516, 0.091946}, {0.021003, 0.105716, 0.053767}};
+// clip_joints limits in degrees (diffusion/diffusion.py:280-298)
+static const double kJointLoDeg[7] = {-166, -101, -166, -176, -166, -1, -166};
+static const double kJointHiDeg[7] = {166, 101, 166, -4, 166, 215, 166};
+
+static bool g_constants_ready = false;
+
+int guide_init_constants() {
+  if (g_constants_ready) return 0;
+  float dh[7][4];
+  for (int i = 0; i < 7; ++i) {
+    float al = (float)kDhHost[i][2];
+    dh[i][0] = (float)kDhHost[i][0];
+    dh[i][1] = (float)kDhHost[i][1];
+    dh[i][2] = cosf(al);
+    dh[i][3] = sinf(al);
+  }
+  float fr[9][12];
+  for (int l = 0; l < 9; ++l) {
+    float r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (l >= 7) {  // hand / finger boxes are yawed -45 deg (lib/guide.py:328-340)
+      r[0] = 7.07106767e-01f; r[1] = 7.07106795e-01f;
+      r[3] = -7.07106795e-01f; r[4] = 7.07106767e-01f;
+    }
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) fr[l][i * 4 + j] = r[i * 3 + j];
+      fr[l][i * 4 + 3] = (float)kFrameT[l][i];
+    }
+  }
+  double lo[7], hi[7];
+  for (int j = 0; j < 7; ++j) {
+    lo[j] = kJointLoDeg[j] * (M_PI / 180);
+    hi[j] = kJointHiDeg[j] * (M_PI / 180);
+  }
+  EDMP_CK(cudaMemcpyToSymbol(c_dh, dh, sizeof(dh)));
+  EDMP_CK(cudaMemcpyToSymbol(c_frame, fr, sizeof(fr)));
+  EDMP_CK(cudaMemcpyToSymbol(c_joint_lo, lo, sizeof(lo)));
+  EDMP_CK(cudaMemcpyToSymbol(c_joint_hi, hi, sizeof(hi)));
+  g_constants_ready = true;
+  return 0;
+}
+
+// ---- device geometry -----------------------------------------------------------------------
+struct Box {
+  float mn[3], mx[3];
+};
+
+// joint frames T[i] (3x4 row major), i = 0..6: T_i = T_{i-1} * DH_i(q_i)
+__device__ void fk_frames(const float q[7], float T[7][12]) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    float s, c;
+    sincosf(q[i], &s, &c);
+    const float a = c_dh[i][0], d = c_dh[i][1], ca = c_dh[i][2], sa = c_dh[i][3];
+    float M[12] = {c,      -s,     0.0f, a,
+                   s * ca, c * ca, -sa,  -sa * d,
+                   s * sa, c * sa, ca,   ca * d};
+    if (i == 0) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) T[0][k] = M[k];
+    } else {
+      const float* P = T[i - 1];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          float v = P[r * 4 + 0] * M[cidx];
+          v = fmaf(P[r * 4 + 1], M[4 + cidx], v);
+          v = fmaf(P[r * 4 + 2], M[8 + cidx], v);
+          if (cidx == 3) v = fmaf(P[r * 4 + 3], 1.0f, v);
+          T[i][r * 4 + cidx] = v;
+        }
+      }
+    }
+  }
+}
+
+// World AABB of link box l; optionally the world positions of the arg-min / arg-max vertex of
+// every axis (pmin[k] / pmax[k], k = axis) for the Jacobian pull.
+template <bool WITH_POS>
+__device__ __forceinline__ void link_box(const float T[7][12], int l, const float* __restrict__ half,
+                                         Box& b, float pmin[3][3], float pmax[3][3]) {
+  const int j = l < 6 ? l : 6;
+  const float* P = T[j];
+  const float* F = c_frame[l];
+  float TL[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = P[r * 4 + 0] * F[c];
+      v = fmaf(P[r * 4 + 1], F[4 + c], v);
+      v = fmaf(P[r * 4 + 2], F[8 + c], v);
+      if (c == 3) v = fmaf(P[r * 4 + 3], 1.0f, v);
+      TL[r * 4 + c] = v;
+    }
+  }
+  const float hx = half[l * 3 + 0], hy = half[l * 3 + 1], hz = half[l * 3 + 2];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    // vertex order of the reference's get_link_vertices (lib/guide.py:203-241)
+    const float vx = ((v & 3) == 1 || (v & 3) == 2) ? hx : -hx;
+    const float vy = (v & 2) ? hy : -hy;
+    const float vz = (v & 4) ? hz : -hz;
+    float p[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float w = TL[r * 4 + 0] * vx;
+      w = fmaf(TL[r * 4 + 1], vy, w);
+      w = fmaf(TL[r * 4 + 2], vz, w);
+      w = fmaf(TL[r * 4 + 3], 1.0f, w);
+      p[r] = w;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (v == 0 || p[k] < b.mn[k]) {
+        b.mn[k] = p[k];
+        if (WITH_POS) { pmin[k][0] = p[0]; pmin[k][1] = p[1]; pmin[k][2] = p[2]; }
+      }
+      if (v == 0 || p[k] > b.mx[k]) {
+        b.mx[k] = p[k];
+        if (WITH_POS) { pmax[k][0] = p[0]; pmax[k][1] = p[1]; pmax[k][2] = p[2]; }
+      }
+    }
+  }
+}
+
+// Obstacle AABBs of one row into shared memory (define_obstacles, lib/guide.py:118-158):
+// size = max(dims, expansion) + clearance (float64), half extents in float32, 8 vertices through
+// the float32 obstacle transform, min/max.
+__device__ void stage_obstacles(const SceneDev* __restrict__ sc, bool use_tables, double expansion,
+                                double clearance, float* s_omin, float* s_omax) {
+  for (int o = threadIdx.x; o < sc->n_obs; o += blockDim.x) {
+    float h[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double sz = sc->dims[o][k];
+      if (use_tables) sz = fmax(sz, expansion) + clearance;
+      h[k] = (float)sz / 2.0f;
+    }
+    const float* R = sc->R[o];
+    float mn[3], mx[3];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const float vx = ((v & 3) == 1 || (v & 3) == 2) ? h[0] : -h[0];
+      const float vy = (v & 2) ? h[1] : -h[1];
+      const float vz = (v & 4) ? h[2] : -h[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float w = R[r * 3 + 0] * vx;
+        w = fmaf(R[r * 3 + 1], vy, w);
+        w = fmaf(R[r * 3 + 2], vz, w);
+        w = fmaf(sc->C[o][r], 1.0f, w);
+        if (v == 0 || w < mn[r]) mn[r] = w;
+        if (v == 0 || w > mx[r]) mx[r] = w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      s_omin[o * 3 + k] = mn[k];
+      s_omax[o * 3 + k] = mx[k];
+    }
+  }
+}
+
+// sum over obstacles of dV/d(bmax_k) (cmax) and -dV/d(bmin_k) (cmin) for V = prod clamp(len, 0)
+__device__ __forceinline__ void face_coefficients(const Box& b, int n_obs, const float* s_omin,
+                                                  const float* s_omax, float cmax[3], float cmin[3]) {
+  cmax[0] = cmax[1] = cmax[2] = 0.0f;
+  cmin[0] = cmin[1] = cmin[2] = 0.0f;
+  for (int o = 0; o < n_obs; ++o) {
+    const float l0 = fminf(b.mx[0], s_omax[o * 3 + 0]) - fmaxf(b.mn[0], s_omin[o * 3 + 0]);
+    const float l1 = fminf(b.mx[1], s_omax[o * 3 + 1]) - fmaxf(b.mn[1], s_omin[o * 3 + 1]);
+    const float l2 = fminf(b.mx[2], s_omax[o * 3 + 2]) - fmaxf(b.mn[2], s_omin[o * 3 + 2]);
+    if (l0 > 0.0f && l1 > 0.0f && l2 > 0.0f) {
+      const float o0 = l1 * l2, o1 = l0 * l2, o2 = l0 * l1;
+      if (b.mx[0] < s_omax[o * 3 + 0]) cmax[0] += o0;
+      if (b.mx[1] < s_omax[o * 3 + 1]) cmax[1] += o1;
+      if (b.mx[2] < s_omax[o * 3 + 2]) cmax[2] += o2;
+      if (b.mn[0] > s_omin[o * 3 + 0]) cmin[0] += o0;
+      if (b.mn[1] > s_omin[o * 3 + 1]) cmin[1] += o1;
+      if (b.mn[2] > s_omin[o * 3 + 2]) cmin[2] += o2;
+    }
+  }
+}
+
+// torch.max(a, b) / torch.min(a, b) backward: the strict winner takes all, exact ties split
+// 1/2 - 1/2.  Ties are common here: clip_joints pins neighbouring waypoints to the same limit.
+__device__ __forceinline__ float share_max(float mine, float other) {
+  return mine > other ? 1.0f : (mine == other ? 0.5f : 0.0f);
+}
+__device__ __forceinline__ float share_min(float mine, float other) {
+  return mine < other ? 1.0f : (mine == other ? 0.5f : 0.0f);
+}
+
+__device__ __forceinline__ void load_waypoint(const double* __restrict__ x, int ld, int off, int wi,
+                                              int n_inner, const float* start, const float* goal,
+                                              bool clip, float q[7]) {
+  // wi in [-1, n_inner]: -1 = start, n_inner = goal (swept_volume_cost pads them, :484-492)
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    if (wi < 0) q[j] = start[j];
+    else if (wi >= n_inner) q[j] = goal[j];
+    else {
+      double v = x[j * ld + off + wi];
+      if (clip) v = fmin(fmax(v, c_joint_lo[j]), c_joint_hi[j]);
+      q[j] = (float)v;
+    }
+  }
+}
+
+struct EndPoints {
+  float start[7], goal[7];
+};
+
+// ---- gradient: raw G (float32) + per-row sum of squares --------------------------------------
+// grid = rows, block = 64 (thread w < n_inner handles interior waypoint w)
+__global__ void __launch_bounds__(64) guide_grad_kernel(const SceneDev* __restrict__ sc,
+                                                        const double* __restrict__ x, int ld, int off,
+                                                        int n_inner, bool clip, EndPoints ep, int t,
+                                                        const double* __restrict__ clearance,
+                                                        const double* __restrict__ expansion,
+                                                        const unsigned char* __restrict__ method,
+                                                        float* __restrict__ raw, double* __restrict__ rowsq) {
+  __shared__ float s_omin[kMaxObs * 3], s_omax[kMaxObs * 3];
+  __shared__ float s_half[27];
+  __shared__ double s_red[2];
+  const int row = blockIdx.x;
+  const int w = threadIdx.x;
+  stage_obstacles(sc, t != 0, t != 0 ? expansion[(size_t)row * kTSteps + t - 1] : 0.0,
+                  t != 0 ? clearance[(size_t)row * kTSteps + t - 1] : 0.0, s_omin, s_omax);
+  if (threadIdx.x < 27) s_half[threadIdx.x] = sc->link_half[threadIdx.x / 3][threadIdx.x % 3];
+  __syncthreads();
+  const bool sv = method[row] != 0;
+  const double* xr = x + (size_t)row * 7 * ld;
+  const int n_obs = sc->n_obs;
+  double sq = 0.0;
+  if (w < n_inner) {
+    float q[7], T[7][12];
+    load_waypoint(xr, ld, off, w, n_inner, ep.start, ep.goal, clip, q);
+    fk_frames(q, T);
+    float g[7] = {0, 0, 0, 0, 0, 0, 0};
+    float Tp[7][12], Tn[7][12];
+    if (sv) {
+      float qq[7];
+      load_waypoint(xr, ld, off, w - 1, n_inner, ep.start, ep.goal, clip, qq);
+      fk_frames(qq, Tp);
+      load_waypoint(xr, ld, off, w + 1, n_inner, ep.start, ep.goal, clip, qq);
+      fk_frames(qq, Tn);
+    }
+    for (int l = 0; l < 9; ++l) {
+      Box b;
+      float pmin[3][3], pmax[3][3];
+      link_box<true>(T, l, s_half, b, pmin, pmax);
+      float cmax[3], cmin[3];
+      if (!sv) {
+        face_coefficients(b, n_obs, s_omin, s_omax, cmax, cmin);
+      } else {
+        Box bp, bn, u;
+        link_box<false>(Tp, l, s_half, bp, nullptr, nullptr);
+        link_box<false>(Tn, l, s_half, bn, nullptr, nullptr);
+        float amax[3], amin[3], bmax_[3], bmin_[3];
+        // segment (w, w+1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(b.mn[k], bn.mn[k]); u.mx[k] = fmaxf(b.mx[k], bn.mx[k]); }
+        face_coefficients(u, n_obs, s_omin, s_omax, amax, amin);
+        // segment (w-1, w)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(bp.mn[k], b.mn[k]); u.mx[k] = fmaxf(bp.mx[k], b.mx[k]); }
+        face_coefficients(u, n_obs, s_omin, s_omax, bmax_, bmin_);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          cmax[k] = amax[k] * share_max(b.mx[k], bn.mx[k]) + bmax_[k] * share_max(b.mx[k], bp.mx[k]);
+          cmin[k] = amin[k] * share_min(b.mn[k], bn.mn[k]) + bmin_[k] * share_min(b.mn[k], bp.mn[k]);
+        }
+      }
+      // Jacobian pull: d p_k / d q_i = (z_i x (p - o_i))_k for joints i <= j(l)
+      const int jl = l < 6 ? l : 6;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (cmax[k] == 0.0f && cmin[k] == 0.0f) continue;
+        const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        for (int i = 0; i <= jl; ++i) {
+          const float z1 = T[i][k1 * 4 + 2], z2 = T[i][k2 * 4 + 2];
+          const float o1 = T[i][k1 * 4 + 3], o2 = T[i][k2 * 4 + 3];
+          const float dmax = z1 * (pmax[k][k2] - o2) - z2 * (pmax[k][k1] - o1);
+          const float dmin = z1 * (pmin[k][k2] - o2) - z2 * (pmin[k][k1] - o1);
+          g[i] += cmax[k] * dmax - cmin[k] * dmin;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      raw[((size_t)row * 7 + j) * n_inner + w] = g[j];
+      sq += (double)g[j] * (double)g[j];
+    }
+  }
+  // deterministic block reduction of the row's sum of squares
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) rowsq[row] = s_red[0] + s_red[1];
+}
+
+// ---- mix with the ensemble Frobenius norm and (optionally) apply the guided update -----------
+// get_gradient :627-629 and diffusion.py:341.  grid = rows, block = 128.
+__global__ void __launch_bounds__(128) guide_apply_kernel(const float* __restrict__ raw,
+                                                          const double* __restrict__ rowsq, int n_inner,
+                                                          int ensemble_rows,
+                                                          const unsigned char* __restrict__ grad_norm,
+                                                          const double* __restrict__ schedule, int t,
+                                                          double* __restrict__ grad_out,
+                                                          double* __restrict__ x, float* __restrict__ xf) {
+  __shared__ double s_red[4];
+  __shared__ float s_norm;
+  const int row = blockIdx.x;
+  const int e0 = (row / ensemble_rows) * ensemble_rows;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < ensemble_rows; r += blockDim.x) s += rowsq[e0 + r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) s_norm = (float)sqrt(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  __syncthreads();
+  const float norm = s_norm;  // np.linalg.norm of a float32 array is float32
+  const double gn = grad_norm[row] ? 1.0 : 0.0;
+  const double scale = x ? schedule[(size_t)row * kTSteps + t - 1] : 0.0;
+  for (int e = threadIdx.x; e < 7 * n_inner; e += blockDim.x) {
+    const float G = raw[(size_t)row * 7 * n_inner + e];
+    // float32 division, float64 mix -- 0/0 = NaN poisons every row of the ensemble like the
+    // reference (SURVEY.md D5 / section 8b "Errors")
+    const double mixed = (1.0 - gn) * (double)G + gn * (double)(G / norm);
+    if (grad_out) grad_out[(size_t)row * 7 * n_inner + e] = mixed;
+    if (x) {
+      const int j = e / n_inner, w = e % n_inner;
+      const size_t idx = (size_t)row * kRowElems + j * kHorizon + 1 + w;
+      const double v = x[idx] - scale * mixed;
+      x[idx] = v;
+      xf[idx] = (float)v;
+    }
+  }
+}
+
+// ---- full volume tensors for the cost()/swept_volume_cost() API --------------------------------
+// grid = (rows), block = 64; thread = waypoint (iv) or segment (sv)
+__global__ void __launch_bounds__(64) guide_volumes_kernel(const SceneDev* __restrict__ sc,
+                                                           const float* __restrict__ q, int n, int mode,
+                                                           EndPoints ep, int t,
+                                                           const double* __restrict__ clearance,
+                                                           const double* __restrict__ expansion,
+                                                           float* __restrict__ vol) {
+  __shared__ float s_omin[kMaxObs * 3], s_omax[kMaxObs * 3];
+  __shared__ float s_half[27];
+  const int row = blockIdx.x;
+  stage_obstacles(sc, t != 0, t != 0 ? expansion[(size_t)row * kTSteps + t - 1] : 0.0,
+                  t != 0 ? clearance[(size_t)row * kTSteps + t - 1] : 0.0, s_omin, s_omax);
+  if (threadIdx.x < 27) s_half[threadIdx.x] = sc->link_half[threadIdx.x / 3][threadIdx.x % 3];
+  __syncthreads();
+  const int n_obs = sc->n_obs;
+  const int n_out = mode ? n + 1 : n;
+  const float* qr = q + (size_t)row * 7 * n;
+  for (int w = threadIdx.x; w < n_out; w += blockDim.x) {
+    float qa[7], qb[7], Ta[7][12], Tb[7][12];
+    // iv: waypoint w.  sv: segment w joins padded waypoints w-1 and w (start | q | goal).
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (!mode) qa[j] = qr[j * n + w];
+      else {
+        qa[j] = (w == 0) ? ep.start[j] : qr[j * n + w - 1];
+        qb[j] = (w == n) ? ep.goal[j] : qr[j * n + w];
+      }
+    }
+    fk_frames(qa, Ta);
+    if (mode) fk_frames(qb, Tb);
+    for (int l = 0; l < 9; ++l) {
+      Box b;
+      link_box<false>(Ta, l, s_half, b, nullptr, nullptr);
+      if (mode) {
+        Box c;
+        link_box<false>(Tb, l, s_half, c, nullptr, nullptr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { b.mn[k] = fminf(b.mn[k], c.mn[k]); b.mx[k] = fmaxf(b.mx[k], c.mx[k]); }
+      }
+      for (int o = 0; o < n_obs; ++o) {
+        float v = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          v *= fmaxf(fminf(b.mx[k], s_omax[o * 3 + k]) - fmaxf(b.mn[k], s_omin[o * 3 + k]), 0.0f);
+        vol[((size_t)row * n_out + w) * (9 * n_obs) + l * n_obs + o] = v;
+      }
+    }
+  }
+}
+
+// ---- best-of-ensemble cost: sum of swept volumes at t = 0 (lib/guide.py:637-653) ---------------
+__global__ void __launch_bounds__(64) guide_final_cost_kernel(const SceneDev* __restrict__ sc,
+                                                              const double* __restrict__ traj, EndPoints ep,
+                                                              float* __restrict__ cost) {
+  __shared__ float s_omin[kMaxObs * 3], s_omax[kMaxObs * 3];
+  __shared__ float s_half[27];
+  __shared__ double s_red[2];
+  const int row = blockIdx.x;
+  stage_obstacles(sc, false, 0.0, 0.0, s_omin, s_omax);
+  if (threadIdx.x < 27) s_half[threadIdx.x] = sc->link_half[threadIdx.x / 3][threadIdx.x % 3];
+  __syncthreads();
+  const int n_obs = sc->n_obs;
+  const double* xr = traj + (size_t)row * kRowElems;
+  double total = 0.0;
+  const int s = threadIdx.x;  // segment s joins waypoints s and s+1 of [start | interior | goal]
+  if (s < kHorizon - 1) {
+    float qa[7], qb[7], Ta[7][12], Tb[7][12];
+    load_waypoint(xr, kHorizon, 1, s - 1, kHorizon - 2, ep.start, ep.goal, false, qa);
+    load_waypoint(xr, kHorizon, 1, s, kHorizon - 2, ep.start, ep.goal, false, qb);
+    fk_frames(qa, Ta);
+    fk_frames(qb, Tb);
+    float acc = 0.0f;
+    for (int l = 0; l < 9; ++l) {
+      Box b, c;
+      link_box<false>(Ta, l, s_half, b, nullptr, nullptr);
+      link_box<false>(Tb, l, s_half, c, nullptr, nullptr);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { b.mn[k] = fminf(b.mn[k], c.mn[k]); b.mx[k] = fmaxf(b.mx[k], c.mx[k]); }
+      for (int o = 0; o < n_obs; ++o) {
+        float v = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          v *= fmaxf(fminf(b.mx[k], s_omax[o * 3 + k]) - fmaxf(b.mn[k], s_omin[o * 3 + k]), 0.0f);
+        acc += v;
+      }
+    }
+    total = (double)acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) cost[row] = (float)(s_red[0] + s_red[1]);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static void quat_xyzw_to_matrix(const double* qin, double R[9]) {
+  // scipy Rotation.from_quat(...).as_matrix() (scalar last, normalised) -- lib/guide.py:143
+  double n = std::sqrt(qin[0] * qin[0] + qin[1] * qin[1] + qin[2] * qin[2] + qin[3] * qin[3]);
+  double x = qin[0] / n, y = qin[1] / n, z = qin[2] / n, w = qin[3] / n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+
+int scene_create(const double* cfg, int n_obs, const double* link_dims, Scene** out) {
+  EDMP_REQUIRE(n_obs >= 1 && n_obs <= kMaxObs, "n_obs must be in 1..64");
+  if (guide_init_constants()) return 1;
+  Scene* s = new Scene();
+  std::memset(&s->host, 0, sizeof(SceneDev));
+  s->host.n_obs = n_obs;
+  for (int o = 0; o < n_obs; ++o) {
+    const double* c = cfg + o * 10;
+    double R[9];
+    quat_xyzw_to_matrix(c + 3, R);
+    for (int k = 0; k < 9; ++k) s->host.R[o][k] = (float)R[k];
+    for (int k = 0; k < 3; ++k) {
+      s->host.C[o][k] = (float)c[k];
+      s->host.dims[o][k] = c[7 + k];
+    }
+  }
+  for (int l = 0; l < 9; ++l)
+    for (int k = 0; k < 3; ++k)
+      s->host.link_half[l][k] = (float)(link_dims ? link_dims[l * 3 + k] : kLinkDims[l][k]) / 2.0f;
+  if (cudaMalloc(&s->dev, sizeof(SceneDev)) != cudaSuccess ||
+      cudaMemcpy(s->dev, &s->host, sizeof(SceneDev), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("scene_create: device allocation/copy failed");
+    delete s;
+    return 1;
+  }
+  *out = s;
+  return 0;
+}
+
+void scene_destroy(Scene* s) {
+  if (!s) return;
+  cudaFree(s->dev);
+  cudaFree(s->clearance); cudaFree(s->expansion); cudaFree(s->schedule);
+  cudaFree(s->method); cudaFree(s->grad_norm);
+  cudaFree(s->raw); cudaFree(s->rowsq); cudaFree(s->zero_tables);
+  delete s;
+}
+
+static int ensure_work(Scene* s, int rows, int n_inner) {
+  size_t need = (size_t)rows * 7 * n_inner;
+  if (need > s->raw_cap) {
+    cudaFree(s->raw);
+    s->raw = nullptr;
+    EDMP_CK(cudaMalloc(&s->raw, need * sizeof(float)));
+    s->raw_cap = need;
+  }
+  if ((size_t)rows > s->rowsq_cap) {
+    cudaFree(s->rowsq);
+    s->rowsq = nullptr;
+    EDMP_CK(cudaMalloc(&s->rowsq, rows * sizeof(double)));
+    s->rowsq_cap = rows;
+  }
+  return 0;
+}
+
+int scene_set_tables(Scene* s, const double* clr, const double* exp_, const double* sched,
+                     const double* method, const double* gnorm, int rows, int ensemble_rows) {
+  EDMP_REQUIRE(rows > 0 && ensemble_rows > 0 && rows % ensemble_rows == 0,
+               "ensemble_rows must divide rows");
+  cudaFree(s->clearance); cudaFree(s->expansion); cudaFree(s->schedule);
+  cudaFree(s->method); cudaFree(s->grad_norm);
+  s->clearance = s->expansion = s->schedule = nullptr;
+  s->method = s->grad_norm = nullptr;
+  size_t nb = (size_t)rows * kTSteps * sizeof(double);
+  EDMP_CK(cudaMalloc(&s->clearance, nb));
+  EDMP_CK(cudaMalloc(&s->expansion, nb));
+  EDMP_CK(cudaMalloc(&s->schedule, nb));
+  EDMP_CK(cudaMalloc(&s->method, rows));
+  EDMP_CK(cudaMalloc(&s->grad_norm, rows));
+  EDMP_CK(cudaMemcpy(s->clearance, clr, nb, cudaMemcpyHostToDevice));
+  EDMP_CK(cudaMemcpy(s->expansion, exp_, nb, cudaMemcpyHostToDevice));
+  EDMP_CK(cudaMemcpy(s->schedule, sched, nb, cudaMemcpyHostToDevice));
+  std::vector<unsigned char> m(rows), g(rows);
+  for (int r = 0; r < rows; ++r) {
+    m[r] = method[r] != 0.0;
+    g[r] = gnorm[r] != 0.0;
+  }
+  EDMP_CK(cudaMemcpy(s->method, m.data(), rows, cudaMemcpyHostToDevice));
+  EDMP_CK(cudaMemcpy(s->grad_norm, g.data(), rows, cudaMemcpyHostToDevice));
+  s->rows = rows;
+  s->ensemble_rows = ensemble_rows;
+  return 0;
+}
+
+static EndPoints make_endpoints(const double* start, const double* goal) {
+  EndPoints ep;
+  for (int j = 0; j < 7; ++j) {
+    ep.start[j] = start ? (float)start[j] : 0.0f;
+    ep.goal[j] = goal ? (float)goal[j] : 0.0f;
+  }
+  return ep;
+}
+
+int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inner, bool clip,
+                          const double* start_h, const double* goal_h, int t, int rows,
+                          double* grad_out, float* raw_out, double* x_state, float* xf_state,
+                          cudaStream_t st) {
+  EDMP_REQUIRE(s->rows == rows, "guide tables were set for a different row count");
+  EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t out of range");
+  EDMP_REQUIRE(n_inner >= 1 && n_inner <= 64, "n_inner must be in 1..64");
+  if (ensure_work(s, rows, n_inner)) return 1;
+  EndPoints ep = make_endpoints(start_h, goal_h);
+  guide_grad_kernel<<<rows, 64, 0, st>>>(s->dev, x, ld, off, n_inner, clip, ep, t, s->clearance,
+                                         s->expansion, s->method, s->raw, s->rowsq);
+  guide_apply_kernel<<<rows, 128, 0, st>>>(s->raw, s->rowsq, n_inner, s->ensemble_rows, s->grad_norm,
+                                           s->schedule, t, grad_out, x_state, xf_state);
+  EDMP_CK(cudaGetLastError());
+  if (raw_out)
+    EDMP_CK(cudaMemcpyAsync(raw_out, s->raw, (size_t)rows * 7 * n_inner * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int guide_volumes_launch(Scene* s, const float* q, const double* start_h, const double* goal_h, int t,
+                         int mode, int rows, int n, float* vol, cudaStream_t st) {
+  EDMP_REQUIRE(t >= 0 && t <= kTSteps, "t out of range");
+  EDMP_REQUIRE(n >= 1, "n must be positive");
+  if (t != 0) EDMP_REQUIRE(s->rows == rows, "guide tables were set for a different row count");
+  EndPoints ep = make_endpoints(start_h, goal_h);
+  guide_volumes_kernel<<<rows, 64, 0, st>>>(s->dev, q, n, mode, ep, t, s->clearance, s->expansion, vol);
+  EDMP_CK(cudaGetLastError());
+  return 0;
+}
+
+int guide_final_cost_launch(Scene* s, const double* traj, const double* start_h, const double* goal_h,
+                            int rows, float* cost, cudaStream_t st) {
+  EndPoints ep = make_endpoints(start_h, goal_h);
+  guide_final_cost_kernel<<<rows, 64, 0, st>>>(s->dev, traj, ep, cost);
+  EDMP_CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace edmp

@@ -1,0 +1,20 @@
+// TemporalUNet engine interface (unet.cu) used by sampler.cu / api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace edmp {
+struct UNet;
+size_t unet_param_count(const int* dims, int n_dims);
+int unet_create(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
+                int max_rows, UNet** out);
+void unet_destroy(UNet* u);
+// eps[rows,7,50] = model(x[rows,7,50], t)
+int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st);
+int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C, int* L, cudaStream_t st);
+int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms, double* macs, float* eps,
+                 cudaStream_t st);
+const char* unet_op_name(const UNet* u, int i);
+int unet_precision(const UNet* u);
+int unet_launches(const UNet* u);
+}  // namespace edmp

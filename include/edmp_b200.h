@@ -1,0 +1,144 @@
+/*
+ * edmp_b200.h -- C ABI of the B200-native guided-diffusion trajectory sampler.
+ *
+ * Drop-in boundary for the hot path of vishal-2000/EDMP (`infer_serial.py`):
+ *   Diffusion.denoise_guided            reference diffusion/diffusion.py:300-356
+ *   TemporalUNet.forward                reference diffusion/models/temporalunet.py:47-76
+ *   IntersectionVolumeGuide.{cost, swept_volume_cost, get_gradient, choose_best_trajectory}
+ *                                       reference lib/guide.py:354-395, :473-537, :597-635, :637-653
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; edmp_last_error() gives the text.
+ *     No C++ exceptions cross this boundary.
+ *   - pointers suffixed _h are HOST pointers, _d are DEVICE pointers (caller owned, on the device
+ *     that was current when the handle was created).  `stream` is a cudaStream_t passed as void*.
+ *   - handles are opaque, one per device, not thread safe (the reference is single threaded and
+ *     keeps per-scene state in the guide object, lib/guide.py:155-156).
+ *   - trajectories are laid out exactly like the reference: [rows, 7, 50] (channels first,
+ *     diffusion/diffusion.py:303).  Sampler state is float64 like the reference's numpy state;
+ *     network input/output is float32 (diffusion.py:319-324).
+ *   - "ensemble" = the rows of one reference denoise_guided call (n_guides x batch_size_per_guide,
+ *     infer_serial.py:56-58).  A batch may hold several ensembles back to back; the whole-batch
+ *     gradient norm (lib/guide.py:629) and the t==1 "row 0 gets no noise" quirk
+ *     (diffusion.py:127) are applied per ensemble.
+ */
+#ifndef EDMP_B200_H
+#define EDMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDMP_T_STEPS 255   /* diffusion steps the tables are sized for (benchmark/cfgs/cfg1.yaml:15) */
+#define EDMP_HORIZON 50    /* waypoints (cfg1.yaml:16)            */
+#define EDMP_DOF 7         /* channels  (cfg1.yaml:17)            */
+#define EDMP_MAX_OBSTACLES 64
+
+typedef struct edmp_unet edmp_unet;       /* packed TemporalUNet weights + activation workspace */
+typedef struct edmp_scene edmp_scene;     /* obstacle set + link boxes + per-row guide tables  */
+typedef struct edmp_sampler edmp_sampler; /* schedule + per-batch state for denoise_guided      */
+
+/* arithmetic used for the convolution contractions */
+enum {
+  EDMP_PRECISION_FP32 = 0,    /* fp32 FMA on CUDA cores (parity mode, always available)          */
+  EDMP_PRECISION_TF32X3 = 1,  /* tcgen05 kind::tf32 with hi/lo operand split (3 MMAs, ~fp32)     */
+  EDMP_PRECISION_TF32 = 2,    /* tcgen05 kind::tf32 single pass (fast, ~1e-3 relative)           */
+  EDMP_PRECISION_BF16X3 = 3,  /* tcgen05 kind::f16 bf16 hi/lo split (3 MMAs, ~2^-16 relative)    */
+  EDMP_PRECISION_BF16 = 4     /* tcgen05 kind::f16 bf16 single pass (fastest, ~1e-2 relative)    */
+};
+
+const char* edmp_last_error(void);
+int edmp_version(void);
+/* number of float32 parameters a TemporalUNet(input_dim=7, time_dim=32, dims) state_dict holds */
+size_t edmp_unet_param_count(const int* dims, int n_dims);
+
+/* ---- TemporalUNet (replaces temporalunet.py:11-45 ctor/load and :47-76 forward) ------------- */
+/* params_h: every tensor of the reference state_dict, flattened and concatenated in state_dict
+ * order (temporalunet.py:78-92 checkpoint layout; 290 tensors / 29,938,471 floats for the
+ * shipped dims (32,64,128,256,512,512)).  max_rows sizes the activation workspace. */
+int edmp_unet_create(const float* params_h, size_t n_params, const int* dims, int n_dims,
+                     int precision, int max_rows, edmp_unet** out);
+void edmp_unet_destroy(edmp_unet* u);
+/* eps[rows,7,50] = model(x[rows,7,50], t), t in 1..255 (one t for the whole batch,
+ * diffusion.py:320).  x_d/eps_d float32 device pointers. */
+int edmp_unet_forward(edmp_unet* u, const float* x_d, int t, int rows, float* eps_d, void* stream);
+/* debug / per-layer parity: copies the activation named like the reference module path
+ * (e.g. "down_samplers.2.down.1", "up_samplers.0.up.3", "final_conv.0") of the LAST forward into
+ * out_d as [rows, C, L] float32; returns C and L. */
+int edmp_unet_read_activation(edmp_unet* u, const char* name, int rows, float* out_d, int* C, int* L,
+                              void* stream);
+/* measurement: per-kernel device time of one forward (CUDA events on `stream` around every launch,
+ * averaged over iters forwards) and the non-padding multiply-accumulates each kernel performs.
+ * ms_h / macs_h hold edmp_unet_launches_per_forward() entries; edmp_unet_op_name(u, i) names op i
+ * after the reference module it implements. */
+int edmp_unet_profile(edmp_unet* u, const float* x_d, int t, int rows, int iters, float* ms_h,
+                      double* macs_h, float* eps_d, void* stream);
+const char* edmp_unet_op_name(const edmp_unet* u, int i);
+int edmp_unet_precision(const edmp_unet* u);
+/* number of kernels one forward launches (for bench.py's gpu_launches claim) */
+int edmp_unet_launches_per_forward(const edmp_unet* u);
+
+/* ---- scene + guide (replaces lib/guide.py:13-43 ctor, :118-158 define_obstacles) ------------ */
+/* obstacle_cfg_h [n_obs,10] = (xyz, quaternion xyzw, dims) float64 (load_test_dataset.py:189);
+ * link_dims_h [9,3] float64 link box extents (lib/guide.py:243-281), NULL = built-in table. */
+int edmp_scene_create(const double* obstacle_cfg_h, int n_obs, const double* link_dims_h,
+                      edmp_scene** out);
+void edmp_scene_destroy(edmp_scene* s);
+/* Per-row guide tables as infer_serial.py:59-91 builds them (float64 host arrays):
+ * clearance/expansion/schedule [rows,255], method/grad_norm [rows] (0/1).  ensemble_rows divides
+ * rows. */
+int edmp_scene_set_guide_tables(edmp_scene* s, const double* clearance_h, const double* expansion_h,
+                                const double* schedule_h, const double* method_h,
+                                const double* grad_norm_h, int rows, int ensemble_rows);
+/* get_gradient (lib/guide.py:597-635): q_d [rows,7,48] float64 (already clipped by the caller, as
+ * diffusion.py:328 does), start_h/goal_h [7] float64, t in 1..255.  grad_d [rows,7,48] float64
+ * receives (1-g)*G + g*G/||G||_F(ensemble).  raw_d (optional, may be NULL) receives the float32
+ * autograd-equivalent G before mixing. */
+int edmp_guide_gradient(edmp_scene* s, const double* q_d, const double* start_h, const double* goal_h,
+                        int t, int rows, double* grad_d, float* raw_d, void* stream);
+/* cost (:354-395, mode 0) / swept_volume_cost (:473-537, mode 1): q_d [rows,7,n] float32, returns
+ * volumes_d [rows, n (iv) | n+1 (sv), 9*n_obs] float32 with index link*n_obs+obs.  t == 0 means no
+ * expansion/clearance; with t == 0 the guide tables need not be set (goal filter,
+ * infer_serial.py:119). */
+int edmp_guide_volumes(edmp_scene* s, const float* q_d, const double* start_h, const double* goal_h,
+                       int t, int mode, int rows, int n, float* volumes_d, void* stream);
+/* choose_best_trajectory (:637-653): traj_d [rows,7,50] float64 -> cost_d[rows] float32 =
+ * sum of swept volumes at t=0. */
+int edmp_guide_final_cost(edmp_scene* s, const double* traj_d, const double* start_h,
+                          const double* goal_h, int rows, float* cost_d, void* stream);
+
+/* ---- sampler (replaces diffusion.py:10-20 schedule, :116-135 posterior, :300-356 loop) ------- */
+int edmp_sampler_create(int T, double variance_thresh, int max_rows, edmp_sampler** out);
+void edmp_sampler_destroy(edmp_sampler* s);
+/* Runs reverse steps t = t_start, t_start-1, ..., t_stop+1 of denoise_guided on x_d
+ * [rows,7,50] float64 in place (full run: t_start=255, t_stop=0; a single teacher-forced step t:
+ * t_start=t, t_stop=t-1).  Endpoints are conditioned on start/goal before the first step
+ * (diffusion.py:306-307) and after every step (:347-349).
+ *   noise_d : float64 [t_start-t_stop, rows, 7, 50], noise_d[k] is z for step t_start-k
+ *             (the reference's np.random draws, diffusion.py:126), or NULL to draw N(0,1) on the
+ *             device from Philox4x32-10 keyed by `seed`.
+ *   scene   : NULL disables guidance (Diffusion.denoise, diffusion.py:253-278).
+ *   final_cost_d : optional [rows] float32, filled with the t=0 swept volume when t_stop == 0.
+ * Guide tables must have been set for exactly `rows` rows. */
+int edmp_sample_guided(edmp_sampler* s, edmp_unet* u, edmp_scene* scene, double* x_d,
+                       const double* start_h, const double* goal_h, const double* noise_d,
+                       uint64_t seed, int rows, int t_start, int t_stop, float* final_cost_d,
+                       void* stream);
+/* Same, end to end from HOST buffers (the call bench.py's e2e leg times): copies x_T in, runs all
+ * steps with device-side Philox noise, copies trajectories [rows,7,50] float64 and costs [rows]
+ * float32 back.  x_h/cost_h should be pinned for full-speed copies. */
+int edmp_sample_guided_host(edmp_sampler* s, edmp_unet* u, edmp_scene* scene, double* x_h,
+                            const double* start_h, const double* goal_h, uint64_t seed, int rows,
+                            float* cost_h, void* stream);
+/* schedule read-back (beta, alpha, alpha_bar, each [T] float64) for host-side checks */
+int edmp_sampler_schedule(const edmp_sampler* s, double* beta_h, double* alpha_h, double* alpha_bar_h);
+/* kernels launched by the last edmp_sample_guided[_host] call */
+long long edmp_sampler_last_launches(const edmp_sampler* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDMP_B200_H */

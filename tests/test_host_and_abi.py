@@ -1,0 +1,101 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from edmp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "edmp_b200.h")).read()
+    declared = set(re.findall(r"\b(edmp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.edmp_version() >= 100
+    dims = (ctypes.c_int * 6)(32, 64, 128, 256, 512, 512)
+    assert lib.edmp_unet_param_count(dims, 6) == 29938471
+
+
+def test_no_cpu_fallback():
+    import torch
+    from edmp_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU box")
+    with pytest.raises(_lib.EdmpError):
+        _lib.require_cuda("cpu")
+    with pytest.raises(_lib.EdmpError):
+        _lib.require_cuda("cuda:0")
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "edmp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_key_table_matches_oracle_layout():
+    from edmp_b200.diffusion import unet_key_table
+    from oracle import weights
+    mine = unet_key_table()
+    ref = [(k, s) for k, s, _ in weights.key_table()]
+    assert mine == ref
+
+
+def test_guide_tables_match_oracle_and_shipped_yaml():
+    from edmp_b200 import build_guide_cfgs, load_guide_hparams
+    from oracle import guide_params, sampler_oracle as so
+    guides = sorted(guide_params.GUIDES)
+    hp = load_guide_hparams(guides, os.path.join(ROOT, "guides") + "/")
+    for n, h in zip(guides, hp):
+        h = dict(h)
+        h.pop("batch_size", None)
+        ref = guide_params.GUIDES[n]
+        assert h["guidance_method"] == ref["guidance_method"] and bool(h["grad_norm"]) == ref["grad_norm"]
+        assert [float(v) for v in h["obstacle_clearance"]["range"]] == ref["obstacle_clearance"]["range"]
+        for k, v in ref["obstacle_expansion"].items():
+            assert [float(x) for x in h["obstacle_expansion"][k]] == [float(x) for x in v]
+        assert h["guidance_schedule"]["type"] == ref["guidance_schedule"]["type"]
+        assert float(h["guidance_schedule"]["scale_val"]) == ref["guidance_schedule"]["scale_val"]
+    a = build_guide_cfgs(hp, 3)
+    b = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], 3)
+    for k in b:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+@pytest.mark.reference
+def test_shipped_yaml_equals_reference_yaml():
+    for f in os.listdir("/root/reference/guides/cfgs"):
+        ref = yaml.safe_load(open(os.path.join("/root/reference/guides/cfgs", f)))
+        mine = yaml.safe_load(open(os.path.join(ROOT, "guides", "cfgs", f)))
+        assert ref == mine, f
+
+
+def test_unet_checkpoint_roundtrip(tmp_path):
+    import torch
+    from edmp_b200 import TemporalUNet
+    from oracle import weights
+    d = str(tmp_path / "TemporalUNetModel255_N50")
+    m = TemporalUNet(d, 7, 32, "cuda:0", dims=(32, 64, 128, 256, 512, 512))
+    assert os.path.isdir(d) and m.losses.size == 0
+    sd = weights.seeded_state_dict(3)
+    m.load_state_dict(sd)
+    m.losses = np.zeros(2)
+    m.save()
+    m2 = TemporalUNet(d, 7, 32, "cuda:0", dims=(32, 64, 128, 256, 512, 512))
+    assert m2.losses.size == 2
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k])
+    assert m2.flat_params().size == 29938471
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("final_conv.1.bias")
+        m2.load_state_dict(bad)
