@@ -1,0 +1,378 @@
+// Tensor-core (tcgen05 + TMEM) convolution kernel for the short-horizon levels of the TemporalUNet
+// (L <= 7: 87 % of the network's multiply-accumulates).
+//
+// GEMM view ("rows as M"):  D[row, (l_out, c_out)] = sum_{(l_in, c_in)} X[row, (l_in, c_in)] * W
+//   * M = 128 trajectory rows per CTA (UMMA_M = 128, cta_group::1), accumulator in TMEM;
+//   * the K axis is ordered (l_in, c_in) and cut into 32-float (128 B) chunks, so one K chunk is
+//     one input position l_in and 32 input channels;
+//   * the N axis of a CTA is ordered (l_out, channel-in-tile); a K chunk at l_in only touches the
+//     output positions within the filter's reach, i.e. a contiguous column window of the
+//     accumulator, so each chunk is ONE windowed tcgen05.mma (N_w = #positions x channels) and no
+//     zero-padding tap is ever multiplied (exactly the non-padding MACs);
+//   * operands are pre-tiled in global memory as ready-made UMMA shared-memory images
+//     (128 rows x 128 B, SWIZZLE_128B, K-major): the producer warp moves them with 1-D bulk async
+//     copies (TMA engine) signalled on mbarriers -- no tensor maps needed;
+//   * fp32 fidelity: every operand exists as a TF32 "hi" part and a TF32 "lo" remainder and each
+//     product is three MMAs (hi*hi + lo*hi + hi*lo), error ~2^-22 ("3xTF32");
+//   * warp roles: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2..5 = epilogue (TMEM -> registers; GroupNorm over the CTA's own columns: a thread owns
+//     one row, so the group statistics are a private serial reduction; Mish; time embedding /
+//     residual; TF32 hi/lo split; stores in the tiled format the next layer consumes).
+//
+// Reference ops covered: Conv1dBlock (blocks.py:13-34), ResidualConvolutionBlock (:137-166) incl.
+// the 1x1 residual conv (second accumulator), stride-2 Conv1d (:211), ConvTranspose1d (:249).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace edmp {
+
+constexpr int kTcRows = 128;        // rows per CTA tile (UMMA M)
+constexpr int kTcChunk = 32;        // floats per K chunk (128 B)
+constexpr int kTcBlock = kTcRows * kTcChunk;   // floats per tiled operand block (16 KB)
+constexpr int kTcMaxLin = 8;
+
+struct TcOperand {      // tiled activation: blocks [row_tile][l * C/32 + c/32][128 x 32 swizzled]
+  const float* hi;
+  const float* lo;
+  int C;
+};
+
+struct TcSched {        // what one K chunk at input position l_in contributes to
+  int8_t slot_begin;    // first weight slot (row block of the packed weight tile)
+  int8_t n_slots;       // number of consecutive output positions touched
+  int8_t lo_begin;      // first output position
+  int8_t pad;
+};
+
+struct TcPhase {
+  TcOperand a, b;       // b.C == 0 unless the input is a skip concat (blocks.py:253)
+  const float* w_hi;    // packed weights [n_tile][c_chunk][slots * ct rows][32] swizzled
+  const float* w_lo;
+  int lin;              // input positions
+  int slots;            // slots stored per weight tile
+  int d_col;            // accumulator column base
+  TcSched sched[kTcMaxLin];
+};
+
+enum TcMode { TC_BIAS = 0, TC_GN = 1, TC_GN_RES_ID = 2, TC_GN_RES_PW = 3 };
+
+struct TcArgs {
+  TcPhase ph[2];
+  int n_phases;
+  int rows, lout, ct, cout;     // ct = channels per CTA column tile; N = lout * ct
+  int mode;
+  int split;                    // 1 = 3xTF32 (hi/lo), 0 = single TF32 pass
+  int a_stages, b_stages;
+  const float *bias, *gamma, *beta, *temb, *bres;
+  TcOperand res;                // identity residual source (tiled)
+  float *out_hi, *out_lo;       // tiled output [row_tile][l*cout/32 + c/32][...], may be null
+  float* out_plain;             // plain [rows][cout][lout], may be null
+};
+
+__device__ __forceinline__ const float* tc_block(const float* base, int C, int lin, int rt, int li, int cc) {
+  return base + ((size_t)rt * (lin * (C >> 5)) + (size_t)li * (C >> 5) + cc) * kTcBlock;
+}
+
+// element (row_local, k) of a tiled block lives at float offset row*32 + ((k/4) ^ (row & 7))*4 + k%4
+__device__ __forceinline__ int tc_swz(int row_local, int chunk16) { return row_local * 32 + ((chunk16 ^ (row_local & 7)) << 2); }
+
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][barriers][params]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nparts = a.split ? 2 : 1;
+  const int a_stage_bytes = kTcBlock * 4 * nparts;
+  int max_slots = a.ph[0].slots;
+  if (a.n_phases > 1 && a.ph[1].slots > max_slots) max_slots = a.ph[1].slots;
+  const int b_part_bytes = max_slots * a.ct * 128;
+  const int b_stage_bytes = b_part_bytes * nparts;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = a_smem + a.a_stages * a_stage_bytes;
+  uint64_t* bars = (uint64_t*)(b_smem + a.b_stages * b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + a.a_stages;
+  uint64_t* b_full = a_empty + a.a_stages;
+  uint64_t* b_empty = b_full + a.b_stages;
+  uint64_t* acc_full = b_empty + a.b_stages;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  float* s_par = (float*)(tmem_slot + 2);   // bias | gamma | beta | temb | bres, 64 floats each
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, nt = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, 1); }
+    umma::mbar_init(acc_full, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;   // 0..127
+    if (e < a.ct) {
+      const int c = nt * a.ct + e;
+      s_par[e] = a.bias[c];
+      s_par[64 + e] = a.gamma ? a.gamma[c] : 1.0f;
+      s_par[128 + e] = a.beta ? a.beta[c] : 0.0f;
+      s_par[192 + e] = a.temb ? a.temb[c] : 0.0f;
+      s_par[256 + e] = a.bres ? a.bres[c] : 0.0f;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: bulk async copies of ready-made operand tiles =====
+    if (lane == 0) {
+      int a_it = 0, b_it = 0;
+      for (int p = 0; p < a.n_phases; ++p) {
+        const TcPhase& ph = a.ph[p];
+        const int ka = ph.a.C >> 5, kb = ph.b.C >> 5;
+        const int wtile_floats = ph.slots * a.ct * kTcChunk;
+        for (int cc = 0; cc < ka + kb; ++cc) {
+          {
+            const int bs = b_it % a.b_stages;
+            umma::mbar_wait(b_empty + bs, ((b_it / a.b_stages) & 1) ^ 1);
+            const uint32_t bytes = (uint32_t)wtile_floats * 4u;
+            umma::mbar_arrive_expect_tx(b_full + bs, bytes * nparts);
+            const size_t woff = ((size_t)nt * (ka + kb) + cc) * wtile_floats;
+            uint8_t* dst = b_smem + bs * b_stage_bytes;
+            umma::bulk_g2s(dst, ph.w_hi + woff, bytes, b_full + bs);
+            if (a.split) umma::bulk_g2s(dst + b_part_bytes, ph.w_lo + woff, bytes, b_full + bs);
+            ++b_it;
+          }
+          for (int li = 0; li < ph.lin; ++li) {
+            if (ph.sched[li].n_slots == 0) continue;
+            const int as = a_it % a.a_stages;
+            umma::mbar_wait(a_empty + as, ((a_it / a.a_stages) & 1) ^ 1);
+            umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
+            const bool first = cc < ka;
+            const TcOperand& op = first ? ph.a : ph.b;
+            const int c2 = first ? cc : cc - ka;
+            uint8_t* dst = a_smem + as * a_stage_bytes;
+            umma::bulk_g2s(dst, tc_block(op.hi, op.C, ph.lin, rt, li, c2), kTcBlock * 4, a_full + as);
+            if (a.split)
+              umma::bulk_g2s(dst + kTcBlock * 4, tc_block(op.lo, op.C, ph.lin, rt, li, c2), kTcBlock * 4,
+                             a_full + as);
+            ++a_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread drives the tensor core =====
+    if (lane == 0) {
+      int a_it = 0, b_it = 0;
+      for (int p = 0; p < a.n_phases; ++p) {
+        const TcPhase& ph = a.ph[p];
+        const int kc_total = (ph.a.C + ph.b.C) >> 5;
+        uint32_t touched = 0;   // output positions whose accumulator columns already hold a partial sum
+        for (int cc = 0; cc < kc_total; ++cc) {
+          const int bs = b_it % a.b_stages;
+          umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
+          const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
+          for (int li = 0; li < ph.lin; ++li) {
+            const TcSched s = ph.sched[li];
+            if (s.n_slots == 0) continue;
+            const int as = a_it % a.a_stages;
+            umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
+            umma::tc_fence_after();
+            const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
+            // first K chunk: the window's positions may differ in "already written", so issue one
+            // MMA per position with its own accumulate flag; afterwards one windowed MMA.
+            const int n_issue = (cc == 0) ? s.n_slots : 1;
+            const int n_cols = ((cc == 0) ? 1 : s.n_slots) * a.ct;
+            const uint32_t idesc = umma::make_idesc(2, kTcRows, n_cols);
+            for (int q = 0; q < n_issue; ++q) {
+              const int lo = s.lo_begin + q;
+              const uint32_t acc0 = (cc == 0) ? ((touched >> lo) & 1u) : 1u;
+              const uint32_t d = tmem_base + (uint32_t)(ph.d_col + lo * a.ct);
+              const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + q) * a.ct * 128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t da_hi = umma::make_desc_sw128(a_base + ks * 32);
+                const uint64_t db_hi = umma::make_desc_sw128(b_off + ks * 32);
+                if (a.split) {
+                  const uint64_t da_lo = umma::make_desc_sw128(a_base + kTcBlock * 4 + ks * 32);
+                  const uint64_t db_lo = umma::make_desc_sw128(b_off + b_part_bytes + ks * 32);
+                  umma::mma_tf32(d, da_lo, db_hi, idesc, (acc0 | (uint32_t)(ks > 0)));
+                  umma::mma_tf32(d, da_hi, db_lo, idesc, 1u);
+                  umma::mma_tf32(d, da_hi, db_hi, idesc, 1u);
+                } else {
+                  umma::mma_tf32(d, da_hi, db_hi, idesc, (acc0 | (uint32_t)(ks > 0)));
+                }
+              }
+              if (cc == 0) touched |= 1u << lo;
+            }
+            umma::mma_commit(a_empty + as);   // frees the A stage once these MMAs have read it
+            ++a_it;
+          }
+          umma::mma_commit(b_empty + bs);
+          ++b_it;
+        }
+      }
+      umma::mma_commit(acc_full);
+    }
+  } else {
+    // ===== epilogue: 4 warps, thread <-> accumulator lane <-> trajectory row =====
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_local = quarter * 32 + lane;
+    const int row = rt * kTcRows + row_local;
+    const bool valid = row < a.rows;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int N = a.lout * a.ct;
+    const int n_units = N >> 4;
+    umma::mbar_wait(acc_full, 0);
+    umma::tc_fence_after();
+
+    float mean = 0.0f, rstd = 1.0f;
+    if (a.mode != TC_BIAS) {
+      // GroupNorm(8): this CTA's columns are exactly one group of this row (blocks.py:24-26)
+      float s = 0.0f;
+      for (int u = 0; u < n_units; ++u) {
+        float v[16];
+        umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
+        const int c0 = (u * 16) % a.ct;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v[i] + s_par[c0 + i];
+      }
+      mean = s / (float)N;
+      float ss = 0.0f;
+      for (int u = 0; u < n_units; ++u) {
+        float v[16];
+        umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
+        const int c0 = (u * 16) % a.ct;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float d = v[i] + s_par[c0 + i] - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+      rstd = 1.0f / sqrtf(ss / (float)N + 1e-5f);
+    }
+    const int kch_out = a.cout >> 5;
+    for (int u = 0; u < n_units; ++u) {
+      float v[16];
+      umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
+      const int lo = (u * 16) / a.ct;
+      const int c0 = (u * 16) % a.ct;
+      const int cglob = nt * a.ct + c0;          // first of 16 consecutive output channels
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float y = v[i] + s_par[c0 + i];
+        if (a.mode != TC_BIAS) {
+          y = (y - mean) * rstd * s_par[64 + c0 + i] + s_par[128 + c0 + i];
+          y = mish_f(y) + s_par[192 + c0 + i];
+        }
+        v[i] = y;
+      }
+      if (a.mode == TC_GN_RES_PW) {
+        float r[16];
+        umma::tmem_ld16(t_lane + a.ph[1].d_col + u * 16, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
+      } else if (a.mode == TC_GN_RES_ID) {
+        // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
+        const int k = lo * a.res.C + cglob;
+        const size_t blk = ((size_t)rt * (a.lout * (a.res.C >> 5)) + (k >> 5)) * kTcBlock;
+        const int j0 = (k & 31) >> 2;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int off = tc_swz(row_local, j0 + m);
+          const float4 h = *reinterpret_cast<const float4*>(a.res.hi + blk + off);
+          float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.res.lo) l = *reinterpret_cast<const float4*>(a.res.lo + blk + off);
+          v[m * 4 + 0] += h.x + l.x;
+          v[m * 4 + 1] += h.y + l.y;
+          v[m * 4 + 2] += h.z + l.z;
+          v[m * 4 + 3] += h.w + l.w;
+        }
+      }
+      if (valid) {
+        if (a.out_hi) {
+          const int k = lo * a.cout + cglob;
+          const size_t blk = ((size_t)rt * (a.lout * kch_out) + (k >> 5)) * kTcBlock;
+          const int j0 = (k & 31) >> 2;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int off = tc_swz(row_local, j0 + m);
+            float4 h, l;
+            if (a.out_lo) {
+              h.x = umma::to_tf32(v[m * 4 + 0]); l.x = umma::to_tf32(v[m * 4 + 0] - h.x);
+              h.y = umma::to_tf32(v[m * 4 + 1]); l.y = umma::to_tf32(v[m * 4 + 1] - h.y);
+              h.z = umma::to_tf32(v[m * 4 + 2]); l.z = umma::to_tf32(v[m * 4 + 2] - h.z);
+              h.w = umma::to_tf32(v[m * 4 + 3]); l.w = umma::to_tf32(v[m * 4 + 3] - h.w);
+              *reinterpret_cast<float4*>(a.out_lo + blk + off) = l;
+            } else {
+              h = make_float4(v[m * 4 + 0], v[m * 4 + 1], v[m * 4 + 2], v[m * 4 + 3]);
+            }
+            *reinterpret_cast<float4*>(a.out_hi + blk + off) = h;
+          }
+        }
+        if (a.out_plain) {
+          float* o = a.out_plain + ((size_t)row * a.cout + cglob) * a.lout + lo;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[(size_t)i * a.lout] = v[i];
+        }
+      }
+    }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// plain [rows][C][L] float32  ->  tiled hi/lo operand blocks (K order (l, c))
+__global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int L, float* __restrict__ hi,
+                               float* __restrict__ lo) {
+  // one thread per (row, l, 4 consecutive channels)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C >> 2;
+  const size_t total = (size_t)rows * L * c4n;
+  if (i >= total) return;
+  const int c4 = (int)(i % c4n);
+  const int l = (int)((i / c4n) % L);
+  const int row = (int)(i / ((size_t)c4n * L));
+  const int rt = row / kTcRows, rl = row % kTcRows;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = x[((size_t)row * C + c4 * 4 + e) * L + l];
+  const int k = l * C + c4 * 4;
+  const size_t blk = ((size_t)rt * (L * (C >> 5)) + (k >> 5)) * kTcBlock;
+  const int off = tc_swz(rl, (k & 31) >> 2);
+  float4 h, r;
+  if (lo) {
+    h.x = umma::to_tf32(v[0]); r.x = umma::to_tf32(v[0] - h.x);
+    h.y = umma::to_tf32(v[1]); r.y = umma::to_tf32(v[1] - h.y);
+    h.z = umma::to_tf32(v[2]); r.z = umma::to_tf32(v[2] - h.z);
+    h.w = umma::to_tf32(v[3]); r.w = umma::to_tf32(v[3] - h.w);
+    *reinterpret_cast<float4*>(lo + blk + off) = r;
+  } else {
+    h = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  *reinterpret_cast<float4*>(hi + blk + off) = h;
+}
+
+// tiled hi/lo -> plain [rows][C][L] (debug read-back and the tensor -> CUDA-core boundary)
+__global__ void tc_unpack_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int rows, int C, int L,
+                                 float* __restrict__ x) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)rows * C * L;
+  if (i >= total) return;
+  const int l = (int)(i % L);
+  const int c = (int)((i / L) % C);
+  const int row = (int)(i / ((size_t)C * L));
+  const int rt = row / kTcRows, rl = row % kTcRows;
+  const int k = l * C + c;
+  const size_t blk = ((size_t)rt * (L * (C >> 5)) + (k >> 5)) * kTcBlock;
+  const int off = tc_swz(rl, (k & 31) >> 2) + (k & 3);
+  x[i] = hi[blk + off] + (lo ? lo[blk + off] : 0.0f);
+}
+
+}  // namespace edmp

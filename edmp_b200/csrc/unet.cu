@@ -9,6 +9,7 @@
 // t = 1..255 and the per-step work is a broadcast add inside the conv epilogue.
 #include "unet.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -17,6 +18,7 @@
 
 #include "common.cuh"
 #include "conv_simt.cuh"
+#include "conv_tc.cuh"
 #include "edmp_b200.h"
 
 namespace edmp {
@@ -180,13 +182,22 @@ size_t unet_param_count(const int* dims, int n_dims) {
 
 // ---- engine -----------------------------------------------------------------------------------------
 struct Act {
-  float* p = nullptr;
+  float* p = nullptr;              // plain [rows][C][L] float32 (CUDA-core layers), may be null
+  float *thi = nullptr, *tlo = nullptr;  // tiled TF32 hi / lo operand blocks (tensor-core layers)
   int C = 0, L = 0;
+  bool ok = true;
 };
 
+enum LayerKind { LAYER_SIMT = 0, LAYER_TC = 1, LAYER_PACK = 2 };
+
 struct Layer {
+  int kind = LAYER_SIMT;
   ConvLaunchFn fn = nullptr;
   ConvArgs args;
+  TcArgs targs;                 // LAYER_TC
+  int tc_tiles = 0;             // column tiles (grid.y) of a tensor-core layer
+  size_t tc_smem = 0;
+  Act pack_src, pack_dst;       // LAYER_PACK
   int temb_off = -1;  // offset into the per-t time-embedding row, -1 = none
   std::string name;   // reference module path of the op
   double macs_per_row = 0.0;  // non-padding multiply-accumulates per trajectory row
@@ -205,6 +216,8 @@ template <int OP> static double count_pairs(int lin, int lout) {
 
 struct UNet {
   int precision = 0;
+  bool tc = false;        // tensor-core path for the L <= 7 levels
+  bool tc_split = false;  // 3xTF32 (hi/lo operands)
   int max_rows = 0;
   int n_launches = 0;
   std::vector<float*> dev_allocs;
@@ -229,14 +242,25 @@ static float* upload(UNet* u, const std::vector<float>& v) {
   return p;
 }
 
-static Act new_act(UNet* u, const std::string& name, int C, int L) {
+static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = true, bool tiled = false) {
   Act a;
   a.C = C; a.L = L;
-  if (cudaMalloc(&a.p, (size_t)u->max_rows * C * L * sizeof(float)) != cudaSuccess) {
-    a.p = nullptr;
-    return a;
+  bool ok = true;
+  if (plain) {
+    ok = cudaMalloc(&a.p, (size_t)u->max_rows * C * L * sizeof(float)) == cudaSuccess;
+    if (ok) u->dev_allocs.push_back(a.p);
   }
-  u->dev_allocs.push_back(a.p);
+  if (ok && tiled) {
+    // row tiles of 128; zero-filled once so the padding rows of the last tile stay finite
+    const size_t n = (size_t)((u->max_rows + kTcRows - 1) / kTcRows) * L * (C / kTcChunk) * kTcBlock;
+    ok = cudaMalloc(&a.thi, n * sizeof(float)) == cudaSuccess;
+    if (ok) { u->dev_allocs.push_back(a.thi); cudaMemset(a.thi, 0, n * sizeof(float)); }
+    if (ok && u->tc_split) {
+      ok = cudaMalloc(&a.tlo, n * sizeof(float)) == cudaSuccess;
+      if (ok) { u->dev_allocs.push_back(a.tlo); cudaMemset(a.tlo, 0, n * sizeof(float)); }
+    }
+  }
+  if (!ok) { a.p = nullptr; a.thi = nullptr; a.ok = false; return a; }
   if (!name.empty()) u->acts[name] = a;
   return a;
 }
@@ -340,6 +364,223 @@ struct Builder {
     return conv_block(p + ".blocks.1", h, nullptr, cout, p, -1, cin != cout ? 2 : 1, &xa, xb, p);
   }
 
+
+  // ---------------- tensor-core (tcgen05) layers ------------------------------------------------
+  static float tf32_round(float x) {   // cvt.rna.tf32.f32 on the host
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    b = (b + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &b, 4);
+    return r;
+  }
+
+  // Packs weights into UMMA-ready tiles [n_tile][c_chunk][slots*ct rows][32 floats], SWIZZLE_128B,
+  // K-major; wfn(co, ci, slot) supplies the value.  Produces the TF32 hi part and (3xTF32) the lo
+  // remainder.
+  template <class F>
+  void pack_tc(int cout, int cin, int ct, int slots, F wfn, const float** hi_out, const float** lo_out) {
+    const int n_tiles = cout / ct, kch = cin / kTcChunk;
+    const size_t tile = (size_t)slots * ct * kTcChunk;
+    std::vector<float> hi(tile * n_tiles * kch), lo(u->tc_split ? hi.size() : 0);
+    for (int nt = 0; nt < n_tiles; ++nt)
+      for (int cc = 0; cc < kch; ++cc) {
+        const size_t base = ((size_t)nt * kch + cc) * tile;
+        for (int sl = 0; sl < slots; ++sl)
+          for (int c = 0; c < ct; ++c) {
+            const int r = sl * ct + c;
+            for (int e = 0; e < kTcChunk; ++e) {
+              const float w = wfn(nt * ct + c, cc * kTcChunk + e, sl);
+              const size_t off = base + (size_t)r * 32 + ((((e >> 2) ^ (r & 7)) << 2) | (e & 3));
+              const float h = tf32_round(w);
+              hi[off] = h;
+              if (u->tc_split) lo[off] = tf32_round(w - h);
+            }
+          }
+      }
+    *hi_out = upload(u, hi);
+    ok = ok && *hi_out;
+    *lo_out = nullptr;
+    if (u->tc_split) {
+      *lo_out = upload(u, lo);
+      ok = ok && *lo_out;
+    }
+  }
+
+  void finish_tc_layer(Layer& ly, int n_tiles) {
+    TcArgs& t = ly.targs;
+    t.split = u->tc_split ? 1 : 0;
+    const int nparts = t.split ? 2 : 1;
+    int max_slots = t.ph[0].slots;
+    if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
+    const size_t a_stage = (size_t)kTcBlock * 4 * nparts;
+    const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
+    const size_t budget = 232448 - 1024 - 2048;   // dynamic smem limit - alignment slack - barriers/params
+    t.b_stages = (2 * b_stage + 2 * a_stage <= budget) ? 2 : 1;
+    size_t rest = budget - t.b_stages * b_stage;
+    t.a_stages = (int)std::min<size_t>(4, rest / a_stage);
+    ok = ok && t.a_stages >= 2;
+    ly.kind = LAYER_TC;
+    ly.tc_tiles = n_tiles;
+    ly.tc_smem = 1024 + t.a_stages * a_stage + t.b_stages * b_stage + 2048;
+  }
+
+  static TcOperand operand(const Act* a) {
+    TcOperand o;
+    o.hi = a ? a->thi : nullptr;
+    o.lo = a ? a->tlo : nullptr;
+    o.C = a ? a->C : 0;
+    return o;
+  }
+
+  // Conv1dBlock on tensor cores; inputs and output are tiled operands.
+  Act tc_conv_block(const std::string& p, const Act& xa, const Act* xb, int cout, const std::string& out_name,
+                    int temb_off, int res, const Act* ra, const Act* rb, const std::string& res_prefix) {
+    const int cin = xa.C + (xb ? xb->C : 0);
+    const int L = xa.L;
+    const int ct = cout / 8;
+    Act y = new_act(u, out_name, cout, L, /*plain=*/false, /*tiled=*/true);
+    ok = ok && y.ok;
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    TcArgs& t = ly.targs;
+    t.n_phases = 1;
+    t.lout = L; t.ct = ct; t.cout = cout;
+    t.mode = res == 0 ? TC_GN : (res == 1 ? TC_GN_RES_ID : TC_GN_RES_PW);
+    TcPhase& ph = t.ph[0];
+    ph.a = operand(&xa);
+    ph.b = operand(xb);
+    ph.lin = L;
+    const int j_begin = std::max(0, 2 - (L - 1)), j_end = std::min(4, 2 + (L - 1));
+    ph.slots = j_end - j_begin + 1;
+    ph.d_col = 0;
+    for (int li = 0; li < L; ++li) {
+      const int lo_min = std::max(0, li - 2), lo_max = std::min(L - 1, li + 2);
+      ph.sched[li].slot_begin = (int8_t)((lo_min - li + 2) - j_begin);
+      ph.sched[li].n_slots = (int8_t)(lo_max - lo_min + 1);
+      ph.sched[li].lo_begin = (int8_t)lo_min;
+    }
+    const float* w = P(p + ".block.0.weight");   // [cout][cin][5]
+    pack_tc(cout, cin, ct, ph.slots,
+            [&](int co, int ci, int sl) { return w[((size_t)co * cin + ci) * 5 + (4 - (j_begin + sl))]; },
+            &ph.w_hi, &ph.w_lo);
+    t.bias = vec(p + ".block.0.bias", cout);
+    t.gamma = vec(p + ".block.2.weight", cout);
+    t.beta = vec(p + ".block.2.bias", cout);
+    ly.temb_off = temb_off;
+    double macs = count_pairs<OP_CONV5>(L, L) * cin * cout;
+    if (res == 1) t.res = operand(ra);
+    if (res == 2) {
+      const int rcin = ra->C + (rb ? rb->C : 0);
+      t.n_phases = 2;
+      TcPhase& pr = t.ph[1];
+      pr.a = operand(ra);
+      pr.b = operand(rb);
+      pr.lin = L;
+      pr.slots = 1;
+      pr.d_col = (L * ct <= 128) ? 128 : 256;
+      for (int li = 0; li < L; ++li) { pr.sched[li].slot_begin = 0; pr.sched[li].n_slots = 1; pr.sched[li].lo_begin = (int8_t)li; }
+      const float* wr = P(res_prefix + ".residual_conv.weight");   // [cout][rcin][1]
+      pack_tc(cout, rcin, ct, 1, [&](int co, int ci, int) { return wr[(size_t)co * rcin + ci]; }, &pr.w_hi, &pr.w_lo);
+      t.bres = vec(res_prefix + ".residual_conv.bias", cout);
+      macs += (double)L * rcin * cout;
+    }
+    t.out_hi = y.thi;
+    t.out_lo = y.tlo;
+    ly.name = p;
+    ly.macs_per_row = macs;
+    finish_tc_layer(ly, 8);
+    u->layers.push_back(ly);
+    return y;
+  }
+
+  Act tc_res_block(const std::string& p, const Act& xa, const Act* xb, int cout) {
+    const int cin = xa.C + (xb ? xb->C : 0);
+    const int off = temb_width;
+    temb_blocks.push_back({p, off});
+    temb_width += cout;
+    Act h = tc_conv_block(p + ".blocks.0", xa, xb, cout, p + ".blocks.0", off, 0, nullptr, nullptr, "");
+    return tc_conv_block(p + ".blocks.1", h, nullptr, cout, p, -1, cin != cout ? 2 : 1, &xa, xb, p);
+  }
+
+  // stride-2 Conv1d / ConvTranspose1d on tensor cores (tiled in; tiled and/or plain out)
+  Act tc_resample(const std::string& name, const Act& x, bool up, bool plain_out) {
+    const int C = x.C, L = x.L;
+    const int lout = up ? ((2 * L == 8 || 2 * L == 14 || 2 * L == 26) ? 2 * L - 1 : 2 * L) : (L + 1) / 2;
+    const int ct = C / 8;
+    Act y = new_act(u, name, C, lout, plain_out, !plain_out);
+    ok = ok && y.ok;
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    TcArgs& t = ly.targs;
+    t.n_phases = 1;
+    t.lout = lout; t.ct = ct; t.cout = C;
+    t.mode = TC_BIAS;
+    TcPhase& ph = t.ph[0];
+    ph.a = operand(&x);
+    ph.b = operand(nullptr);
+    ph.lin = L;
+    ph.d_col = 0;
+    const float* w = P(name + ".weight");
+    if (!up) {
+      // Conv1d(k=3, s=2, p=1): l_in = 2 l_out + tap - 1.  slots: 0 = tap 2, 1 = tap 0, 2 = tap 1
+      ph.slots = 3;
+      for (int li = 0; li < L; ++li) {
+        if (li & 1) {
+          ph.sched[li].slot_begin = 0;
+          ph.sched[li].n_slots = (int8_t)(((li + 1) / 2 < lout) ? 2 : 1);
+          ph.sched[li].lo_begin = (int8_t)((li - 1) / 2);
+        } else {
+          ph.sched[li].slot_begin = 2;
+          ph.sched[li].n_slots = 1;
+          ph.sched[li].lo_begin = (int8_t)(li / 2);
+        }
+      }
+      static const int tap_of_slot[3] = {2, 0, 1};
+      pack_tc(C, C, ct, 3, [&](int co, int ci, int sl) { return w[((size_t)co * C + ci) * 3 + tap_of_slot[sl]]; },
+              &ph.w_hi, &ph.w_lo);
+    } else {
+      // ConvTranspose1d(k=4, s=2, p=1): l_out = 2 l_in - 1 + tap; weight [cin][cout][4]
+      ph.slots = 4;
+      for (int li = 0; li < L; ++li) {
+        const int tmin = li == 0 ? 1 : 0;
+        int tmax = 3;
+        while (2 * li - 1 + tmax >= lout) --tmax;
+        ph.sched[li].slot_begin = (int8_t)tmin;
+        ph.sched[li].n_slots = (int8_t)(tmax - tmin + 1);
+        ph.sched[li].lo_begin = (int8_t)(2 * li - 1 + tmin);
+      }
+      pack_tc(C, C, ct, 4, [&](int co, int ci, int sl) { return w[((size_t)ci * C + co) * 4 + sl]; }, &ph.w_hi,
+              &ph.w_lo);
+    }
+    t.bias = vec(name + ".bias", C);
+    t.out_hi = y.thi;
+    t.out_lo = y.tlo;
+    t.out_plain = y.p;
+    ly.name = name;
+    ly.macs_per_row = (up ? count_pairs<OP_UP4>(L, lout) : count_pairs<OP_DOWN3>(L, lout)) * C * C;
+    finish_tc_layer(ly, 8);
+    u->layers.push_back(ly);
+    return y;
+  }
+
+  // plain -> tiled operand conversion at the CUDA-core / tensor-core boundary
+  Act pack_to_tiled(const Act& x, const std::string& name) {
+    Act y = new_act(u, "", x.C, x.L, false, true);
+    ok = ok && y.ok;
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    ly.kind = LAYER_PACK;
+    ly.pack_src = x;
+    ly.pack_dst = y;
+    ly.name = name + " (tile)";
+    u->layers.push_back(ly);
+    return y;
+  }
+
   Act resample(const std::string& name, const Act& x, bool up) {
     const int C = x.C;
     const int lout = up ? ((2 * x.L == 8 || 2 * x.L == 14 || 2 * x.L == 26) ? 2 * x.L - 1 : 2 * x.L)
@@ -367,7 +608,9 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   EDMP_REQUIRE(n_dims == 6 && dims[0] == 32 && dims[1] == 64 && dims[2] == 128 && dims[3] == 256 &&
                    dims[4] == 512 && dims[5] == 512,
                "only dims=(32,64,128,256,512,512) is compiled in (infer_serial.py:50)");
-  EDMP_REQUIRE(precision == EDMP_PRECISION_FP32, "this build only has the fp32 CUDA-core path");
+  EDMP_REQUIRE(precision == EDMP_PRECISION_FP32 || precision == EDMP_PRECISION_TF32X3 ||
+                   precision == EDMP_PRECISION_TF32,
+               "precision must be fp32, tf32x3 or tf32 (bf16 modes are not built yet)");
   EDMP_REQUIRE(max_rows > 0, "max_rows must be positive");
   ParamWalker pw;
   walk_params(dims, n_dims, pw);
@@ -376,6 +619,15 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   UNet* u = new UNet();
   u->precision = precision;
   u->max_rows = max_rows;
+  u->tc = precision != EDMP_PRECISION_FP32;
+  u->tc_split = precision == EDMP_PRECISION_TF32X3;
+  if (u->tc) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_set = true;
+    }
+  }
   Builder b{u, params, &pw};
   std::vector<int> d(1, kDof);
   for (int i = 0; i < n_dims; ++i) d.push_back(dims[i]);
@@ -384,23 +636,45 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   b.ok = b.ok && x.p;
   std::vector<Act> skips;
   const int n_down = (int)d.size() - 1;
+  // Levels with horizon <= 7 (87 % of the MACs) run on tensor cores when precision != fp32; the
+  // long-horizon, few-channel levels stay on the CUDA-core kernels.
+  auto on_tc = [&](const Act& a) { return u->tc && a.L <= 7; };
   for (int i = 0; i < n_down; ++i) {
     const std::string p = "down_samplers." + std::to_string(i) + ".down.";
-    x = b.res_block(p + "0", x, nullptr, d[i + 1]);
-    x = b.res_block(p + "1", x, nullptr, d[i + 1]);
+    if (on_tc(x)) {
+      if (!x.thi) x = b.pack_to_tiled(x, p + "0");
+      x = b.tc_res_block(p + "0", x, nullptr, d[i + 1]);
+      x = b.tc_res_block(p + "1", x, nullptr, d[i + 1]);
+    } else {
+      x = b.res_block(p + "0", x, nullptr, d[i + 1]);
+      x = b.res_block(p + "1", x, nullptr, d[i + 1]);
+    }
     skips.push_back(x);
-    if (i != n_down - 1) x = b.resample(p + "3", x, false);
+    if (i != n_down - 1) x = on_tc(x) ? b.tc_resample(p + "3", x, false, false) : b.resample(p + "3", x, false);
   }
-  x = b.res_block("middle_block.middle.0", x, nullptr, d.back());
-  x = b.res_block("middle_block.middle.2", x, nullptr, d.back());
+  if (on_tc(x)) {
+    x = b.tc_res_block("middle_block.middle.0", x, nullptr, d.back());
+    x = b.tc_res_block("middle_block.middle.2", x, nullptr, d.back());
+  } else {
+    x = b.res_block("middle_block.middle.0", x, nullptr, d.back());
+    x = b.res_block("middle_block.middle.2", x, nullptr, d.back());
+  }
   int n = 0;
   for (int i = (int)d.size() - 1; i > 1; --i, ++n) {
     const std::string p = "up_samplers." + std::to_string(n) + ".up.";
     Act h = skips.back();
     skips.pop_back();
-    x = b.res_block(p + "0", x, &h, d[i - 1]);
-    x = b.res_block(p + "1", x, nullptr, d[i - 1]);
-    x = b.resample(p + "3", x, true);
+    if (on_tc(x)) {
+      x = b.tc_res_block(p + "0", x, &h, d[i - 1]);
+      x = b.tc_res_block(p + "1", x, nullptr, d[i - 1]);
+      // the up-sampled output feeds a CUDA-core level when it is longer than 7
+      const int lup = (2 * x.L == 8 || 2 * x.L == 14 || 2 * x.L == 26) ? 2 * x.L - 1 : 2 * x.L;
+      x = b.tc_resample(p + "3", x, true, /*plain_out=*/lup > 7);
+    } else {
+      x = b.res_block(p + "0", x, &h, d[i - 1]);
+      x = b.res_block(p + "1", x, nullptr, d[i - 1]);
+      x = b.resample(p + "3", x, true);
+    }
   }
   x = b.conv_block("final_conv.0", x, nullptr, d[1], "final_conv.0", -1, 0, nullptr, nullptr, "");
   u->final_in = x;
@@ -451,19 +725,33 @@ void unet_destroy(UNet* u) {
 int unet_precision(const UNet* u) { return u->precision; }
 int unet_launches(const UNet* u) { return u->n_launches; }
 
-int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st) {
-  EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
-  EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
-  const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
+static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row, int rows, cudaStream_t st) {
   const float* input_act = u->acts.at("input").p;
-  for (Layer& ly : u->layers) {
+  if (ly.kind == LAYER_SIMT) {
     ConvArgs a = ly.args;
     a.rows = rows;
     if (a.xa == input_act) a.xa = x;   // the first block reads (and its residual re-reads) the caller's x
     if (a.ra == input_act) a.ra = x;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     ly.fn(a, st);
+  } else if (ly.kind == LAYER_TC) {
+    TcArgs a = ly.targs;
+    a.rows = rows;
+    a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
+    dim3 grid((rows + kTcRows - 1) / kTcRows, ly.tc_tiles);
+    conv_tc_kernel<<<grid, 192, ly.tc_smem, st>>>(a);
+  } else {
+    const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / 4);
+    tc_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C,
+                                                                  ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
   }
+}
+
+int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st) {
+  EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
+  EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
+  const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
+  for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, st);
   const int threads = 128;
   const size_t n = (size_t)rows * kHorizon;
   final_pw_kernel<<<(unsigned)((n + threads - 1) / threads), threads, (7 * u->final_c + 7) * sizeof(float), st>>>(
@@ -483,17 +771,10 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
   for (auto& e : ev) EDMP_CK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
-  const float* input_act = u->acts.at("input").p;
   for (int it = 0; it < iters; ++it) {
     EDMP_CK(cudaEventRecord(ev[0], st));
     for (int i = 0; i < n - 1; ++i) {
-      Layer& ly = u->layers[i];
-      ConvArgs a = ly.args;
-      a.rows = rows;
-      if (a.xa == input_act) a.xa = x;
-      if (a.ra == input_act) a.ra = x;
-      a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
-      ly.fn(a, st);
+      run_layer(u, u->layers[i], x, temb_row, rows, st);
       EDMP_CK(cudaEventRecord(ev[i + 1], st));
     }
     const size_t ne = (size_t)rows * kHorizon;
@@ -526,9 +807,16 @@ int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace");
   if (C) *C = it->second.C;
   if (L) *L = it->second.L;
-  if (out)
-    EDMP_CK(cudaMemcpyAsync(out, it->second.p, (size_t)rows * it->second.C * it->second.L * sizeof(float),
-                            cudaMemcpyDeviceToDevice, st));
+  if (out) {
+    const Act& a = it->second;
+    const size_t n = (size_t)rows * a.C * a.L;
+    if (a.p) {
+      EDMP_CK(cudaMemcpyAsync(out, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      tc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
+      EDMP_CK(cudaGetLastError());
+    }
+  }
   return 0;
 }
 

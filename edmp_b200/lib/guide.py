@@ -59,6 +59,8 @@ class IntersectionVolumeGuide:
         self.link_dimensions = link_dimensions if link_dimensions is not None else _default_link_dimensions()
         self._scene = None
         self._tables_key = None
+        #: rows per ensemble when one batch holds several (None = the whole batch is one ensemble)
+        self.ensemble_rows = None
 
     def rearrange_joints(self, x):
         # 'batch channels traj_len -> batch traj_len channels' (lib/guide.py:43)
@@ -85,6 +87,8 @@ class IntersectionVolumeGuide:
         scene = self._scene_handle()
         rows = int(rows if rows is not None else self.batch_size)
         sched = guidance_schedule if guidance_schedule is not None else self.guide_cfgs["guidance_schedule"]
+        if ensemble_rows is None:
+            ensemble_rows = self.ensemble_rows
         ens = int(ensemble_rows if ensemble_rows is not None else rows)
         key = (rows, ens, id(sched))
         if self._tables_key != key:

@@ -14,10 +14,13 @@ DEV = "cuda:0"
 DIMS = (32, 64, 128, 256, 512, 512)
 
 
-def _model(tmp_path_factory, sd):
+PRECISIONS = os.environ.get("EDMP_TEST_PRECISIONS", "fp32,tf32x3").split(",")
+
+
+def _model(tmp_path_factory, sd, precision="fp32"):
     from edmp_b200 import TemporalUNet
     d = tmp_path_factory.mktemp("model")
-    m = TemporalUNet(str(d / "TemporalUNetModel255_N50"), 7, 32, DEV, dims=DIMS)
+    m = TemporalUNet(str(d / "TemporalUNetModel255_N50"), 7, 32, DEV, dims=DIMS, precision=precision)
     m.load_state_dict(sd)
     return m
 
@@ -32,14 +35,15 @@ def sd02():
     return weights.seeded_state_dict(0, final_gain=0.2)
 
 
-@pytest.fixture(scope="module")
-def model(tmp_path_factory, sd):
-    return _model(tmp_path_factory, sd)
+@pytest.fixture(scope="module", params=PRECISIONS)
+def model(request, tmp_path_factory, sd):
+    """fp32 = CUDA-core kernels everywhere; tf32x3 = tcgen05 kernels (3xTF32) for the L <= 7 levels."""
+    return _model(tmp_path_factory, sd, request.param)
 
 
-@pytest.fixture(scope="module")
-def model02(tmp_path_factory, sd02):
-    return _model(tmp_path_factory, sd02)
+@pytest.fixture(scope="module", params=PRECISIONS)
+def model02(request, tmp_path_factory, sd02):
+    return _model(tmp_path_factory, sd02, request.param)
 
 
 def _cfgs(guides, bpg):
@@ -67,7 +71,7 @@ def test_unet_matches_reference_fixture(golden, model):
                     assert np.abs(act - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
 
 
-@pytest.mark.parametrize("rows", [1, 37, 130])
+@pytest.mark.parametrize("rows", [1, 37, 130, 257])
 def test_unet_matches_oracle_ragged_rows(model, sd, rows):
     x = torch.randn(rows, 7, 50, generator=torch.Generator().manual_seed(rows)) * 1.5
     with torch.no_grad():
@@ -179,7 +183,7 @@ def test_guide_ensembles_are_independent():
     gb = single.get_gradient(qb, scenes.START, scenes.GOAL, 100)
     both_cfg = {k: (np.concatenate([v, v]) if isinstance(v, np.ndarray) else v) for k, v in cfg1.items()}
     both = IntersectionVolumeGuide(scene, DEV, both_cfg, 12)
-    both.scene_handle(rows=12, ensemble_rows=6)
+    both.ensemble_rows = 6
     gab = both.get_gradient(np.concatenate([qa, qb]), scenes.START, scenes.GOAL, 100)
     assert np.array_equal(gab[:6], ga) and np.array_equal(gab[6:], gb)
 
