@@ -7,8 +7,8 @@
 A "step" is ONE pass of the hot path over one batch: the full 255-step guided reverse diffusion
 (TemporalUNet + posterior + guide gradient/update) of every trajectory row of the batch, followed
 by the per-row best-of-ensemble cost.  Workload (BASELINE.json configs[1]): per GPU
-one ensemble of the first ten shipped guides [1,2,3,4,5,9,10,11,12,13] x 103 rows = 1030
-trajectories (8 GPUs: 8240 >= the 8192 the config names), 20 synthetic obstacles, seeded random
+one ensemble of the first ten shipped guides [1,2,3,4,5,9,10,11,12,13] x 102 rows = 1020
+trajectories (8 row tiles of 128; 8 GPUs: 8160 ~ the 8192 the config names), 20 synthetic obstacles, seeded random
 weights; weak scaling, ensembles rank-local, one NCCL all-gather of the per-row final costs.
 
 Prints ONE JSON line (rank 0).  `value` = trajectories/s with inputs resident in HBM;
@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GUIDES = [1, 2, 3, 4, 5, 9, 10, 11, 12, 13]
-ROWS_PER_GUIDE = 103
+ROWS_PER_GUIDE = 102
 N_OBSTACLES = 20
 USEFUL_GFLOP_PER_ROW_STEP = 0.1222     # 61,096,192 non-padding MACs
 METRIC = "trajectories/sec (255-step, 50x7-DoF, guided ensemble)"
@@ -313,7 +313,7 @@ def run_gpu_arm(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
                 "config": workload_config(world, precision=args.precision),
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": rows * 350 * 8,
@@ -332,7 +332,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "tf32x3"),
+                    help="fp32 (CUDA cores) | tf32x3 (tcgen05, 3xTF32, parity grade) | tf32 (tcgen05 single pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

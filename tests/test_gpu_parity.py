@@ -68,7 +68,10 @@ def test_unet_matches_reference_fixture(golden, model):
                     act = model.read_activation(name, 3).cpu().numpy()
                     ref = g[key][:, :, :act.shape[2]]
                     assert act.shape == ref.shape
-                    assert np.abs(act - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
+                    # fp32 FMA path: accumulation-order noise only.  3xTF32: the tensor core's fp32
+                    # accumulator truncates on every MMA, ~3e-6 relative per layer.
+                    tol = 2e-5 if model.precision == "fp32" else 6e-5
+                    assert np.abs(act - ref).max() <= tol * max(1.0, np.abs(ref).max()), name
 
 
 @pytest.mark.parametrize("rows", [1, 37, 130, 257])
