@@ -298,6 +298,10 @@ def run_gpu_arm(args):
                                     peaks["source"]),
                     "kernel_ms": float(ms[top]), "kernel_share_of_unet": float(ms[top] / ms.sum()),
                     "useful_flops_per_launch": float(2.0 * macs[top])}
+        if args.ops_out:
+            with open(args.ops_out, "w") as f:
+                for nm, m, mc in zip(names, ms, macs):
+                    f.write("%-44s %9.1f us %8.2f useful TFLOP/s\n" % (nm, m * 1e3, 2 * mc / (m * 1e-3) / 1e12 if m > 0 else 0))
         unet_summary = {"ms_per_forward": float(ms.sum()), "useful_tflops": float(2.0 * macs.sum() / (ms.sum() * 1e-3) / 1e12),
                         "launches": int(n_ops)}
 
@@ -335,6 +339,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "tf32x3"),
                     help="fp32 (CUDA cores) | tf32x3 (tcgen05, 3xTF32, parity grade) | tf32 (tcgen05 single pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-out", default=None, help="write the per-kernel time table of one UNet forward here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

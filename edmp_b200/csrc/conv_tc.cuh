@@ -30,7 +30,8 @@ namespace edmp {
 constexpr int kTcRows = 128;        // rows per CTA tile (UMMA M)
 constexpr int kTcChunk = 32;        // floats per K chunk (128 B)
 constexpr int kTcBlock = kTcRows * kTcChunk;   // floats per tiled operand block (16 KB)
-constexpr int kTcMaxLin = 8;
+constexpr int kTcMaxLin = 13;
+constexpr int kTcThreads = 64 + 256;  // producer warp, MMA warp, 8 epilogue warps
 
 struct TcOperand {      // tiled activation: blocks [row_tile][l * C/32 + c/32][128 x 32 swizzled]
   const float* hi;
@@ -61,6 +62,7 @@ struct TcArgs {
   TcPhase ph[2];
   int n_phases;
   int rows, lout, ct, cout;     // ct = channels per CTA column tile; N = lout * ct
+  int cg;                       // channels per GroupNorm group (ct / cg groups per column tile, 1 or 2)
   int mode;
   int split;                    // 1 = 3xTF32 (hi/lo), 0 = single TF32 pass
   int a_stages, b_stages;
@@ -77,7 +79,17 @@ __device__ __forceinline__ const float* tc_block(const float* base, int C, int l
 // element (row_local, k) of a tiled block lives at float offset row*32 + ((k/4) ^ (row & 7))*4 + k%4
 __device__ __forceinline__ int tc_swz(int row_local, int chunk16) { return row_local * 32 + ((chunk16 ^ (row_local & 7)) << 2); }
 
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+// Mish with hardware exp2 / reciprocal approximations (rel. error ~1e-6, below the 3xTF32
+// accumulation error); the CUDA-core path keeps the accurate version.
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = __expf(fminf(x, 20.0f));
+  const float n = e * (e + 2.0f);
+  return x > 20.0f ? x : x * __fdividef(n, n + 2.0f);
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][params]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -97,6 +109,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* acc_full = b_empty + a.b_stages;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
   float* s_par = (float*)(tmem_slot + 2);   // bias | gamma | beta | temb | bres, 64 floats each
+  float* s_stat = s_par + 320;              // [pass 2][half 2][group 2][128 rows] partial GroupNorm sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, nt = blockIdx.y;
@@ -109,7 +122,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   }
   if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
   if (warp >= 2) {
-    const int e = threadIdx.x - 64;   // 0..127
+    const int e = threadIdx.x - 64;   // 0..255
     if (e < a.ct) {
       const int c = nt * a.ct + e;
       s_par[e] = a.bias[c];
@@ -217,44 +230,70 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       umma::mma_commit(acc_full);
     }
   } else {
-    // ===== epilogue: 4 warps, thread <-> accumulator lane <-> trajectory row =====
+    // ===== epilogue: 8 warps; a thread owns one accumulator lane (trajectory row) and every other
+    // 16-column unit of it (two warps share each 32-lane TMEM quarter) =====
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the column units
     const int row_local = quarter * 32 + lane;
     const int row = rt * kTcRows + row_local;
     const bool valid = row < a.rows;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int N = a.lout * a.ct;
     const int n_units = N >> 4;
+    const int gpt = a.ct / a.cg;                  // GroupNorm groups in this column tile (1 or 2)
     umma::mbar_wait(acc_full, 0);
     umma::tc_fence_after();
 
-    float mean = 0.0f, rstd = 1.0f;
+    float mean[2] = {0.0f, 0.0f}, rstd[2] = {1.0f, 1.0f};
     if (a.mode != TC_BIAS) {
-      // GroupNorm(8): this CTA's columns are exactly one group of this row (blocks.py:24-26)
-      float s = 0.0f;
-      for (int u = 0; u < n_units; ++u) {
+      // GroupNorm(8) over (cg channels x lout positions) of this row (blocks.py:24-26): two-pass,
+      // partial sums of the two column halves meet in shared memory
+      const float inv_n = 1.0f / (float)(a.cg * a.lout);
+      float s[2] = {0.0f, 0.0f};
+      for (int u = half; u < n_units; u += 2) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int c0 = (u * 16) % a.ct;
+        if (gpt == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += v[i] + s_par[c0 + i];
-      }
-      mean = s / (float)N;
-      float ss = 0.0f;
-      for (int u = 0; u < n_units; ++u) {
-        float v[16];
-        umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
-        const int c0 = (u * 16) % a.ct;
+          for (int i = 0; i < 16; ++i) s[0] += v[i] + s_par[c0 + i];
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float d = v[i] + s_par[c0 + i] - mean;
-          ss = fmaf(d, d, ss);
+          for (int i = 0; i < 8; ++i) { s[0] += v[i] + s_par[c0 + i]; s[1] += v[8 + i] + s_par[c0 + 8 + i]; }
         }
       }
-      rstd = 1.0f / sqrtf(ss / (float)N + 1e-5f);
+      s_stat[(half * 2 + 0) * 128 + row_local] = s[0];
+      s_stat[(half * 2 + 1) * 128 + row_local] = s[1];
+      epi_barrier();
+      mean[0] = (s_stat[0 * 128 + row_local] + s_stat[2 * 128 + row_local]) * inv_n;
+      mean[1] = (s_stat[1 * 128 + row_local] + s_stat[3 * 128 + row_local]) * inv_n;
+      float ss[2] = {0.0f, 0.0f};
+      for (int u = half; u < n_units; u += 2) {
+        float v[16];
+        umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
+        const int c0 = (u * 16) % a.ct;
+        if (gpt == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float d = v[i] + s_par[c0 + i] - mean[0]; ss[0] = fmaf(d, d, ss[0]); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d0 = v[i] + s_par[c0 + i] - mean[0];
+            const float d1 = v[8 + i] + s_par[c0 + 8 + i] - mean[1];
+            ss[0] = fmaf(d0, d0, ss[0]);
+            ss[1] = fmaf(d1, d1, ss[1]);
+          }
+        }
+      }
+      float* s2 = s_stat + 512;
+      s2[(half * 2 + 0) * 128 + row_local] = ss[0];
+      s2[(half * 2 + 1) * 128 + row_local] = ss[1];
+      epi_barrier();
+      rstd[0] = rsqrtf((s2[0 * 128 + row_local] + s2[2 * 128 + row_local]) * inv_n + 1e-5f);
+      rstd[1] = rsqrtf((s2[1 * 128 + row_local] + s2[3 * 128 + row_local]) * inv_n + 1e-5f);
     }
     const int kch_out = a.cout >> 5;
-    for (int u = 0; u < n_units; ++u) {
+    for (int u = half; u < n_units; u += 2) {
       float v[16];
       umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
       const int lo = (u * 16) / a.ct;
@@ -264,8 +303,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       for (int i = 0; i < 16; ++i) {
         float y = v[i] + s_par[c0 + i];
         if (a.mode != TC_BIAS) {
-          y = (y - mean) * rstd * s_par[64 + c0 + i] + s_par[128 + c0 + i];
-          y = mish_f(y) + s_par[192 + c0 + i];
+          const int g = (gpt == 2 && i >= 8) ? 1 : 0;
+          y = (y - mean[g]) * rstd[g] * s_par[64 + c0 + i] + s_par[128 + c0 + i];
+          y = mish_fast(y) + s_par[192 + c0 + i];
         }
         v[i] = y;
       }
