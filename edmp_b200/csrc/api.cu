@@ -65,6 +65,10 @@ int edmp_unet_profile(edmp_unet* u, const float* x_d, int t, int rows, int iters
   if (!u || !x_d || !ms_h || !macs_h || !eps_d) { set_error("edmp_unet_profile: null argument"); return 2; }
   EDMP_TRY(unet_profile(u->impl, x_d, t, rows, iters, ms_h, macs_h, eps_d, (cudaStream_t)stream));
 }
+int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, void* stream) {
+  if (!u || !out_h || !n_ctas) { set_error("edmp_unet_tc_trace: null argument"); return 2; }
+  EDMP_TRY(unet_tc_trace(u->impl, op, rows, out_h, max_ctas, n_ctas, (cudaStream_t)stream));
+}
 const char* edmp_unet_op_name(const edmp_unet* u, int i) { return u ? unet_op_name(u->impl, i) : nullptr; }
 int edmp_unet_precision(const edmp_unet* u) { return u ? unet_precision(u->impl) : -1; }
 int edmp_unet_launches_per_forward(const edmp_unet* u) { return u ? unet_launches(u->impl) : 0; }

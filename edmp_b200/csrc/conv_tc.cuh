@@ -66,10 +66,13 @@ struct TcArgs {
   int mode;
   int split;                    // 1 = 3xTF32 (hi/lo), 0 = single TF32 pass
   int a_stages, b_stages;
+  int epi_units;                // 16-column units staged in shared memory per epilogue round (even)
+  int stage_bytes;              // bytes reserved for operand stages / epilogue staging (barriers follow)
   const float *bias, *gamma, *beta, *temb, *bres;
   TcOperand res;                // identity residual source (tiled)
   float *out_hi, *out_lo;       // tiled output [row_tile][l*cout/32 + c/32][...], may be null
   float* out_plain;             // plain [rows][cout][lout], may be null
+  long long* dbg;               // optional [ctas][8] clock64 stamps (tools/tc_debug.py), normally null
 };
 
 __device__ __forceinline__ const float* tc_block(const float* base, int C, int lin, int rt, int li, int cc) {
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int b_stage_bytes = b_part_bytes * nparts;
   uint8_t* a_smem = smem;
   uint8_t* b_smem = a_smem + a.a_stages * a_stage_bytes;
-  uint64_t* bars = (uint64_t*)(b_smem + a.b_stages * b_stage_bytes);
+  uint64_t* bars = (uint64_t*)(smem + a.stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + a.a_stages;
   uint64_t* b_full = a_empty + a.a_stages;
@@ -113,6 +116,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, nt = blockIdx.y;
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); }
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== producer: bulk async copies of ready-made operand tiles =====
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         for (int cc = 0; cc < kc_total; ++cc) {
           const int bs = b_it % a.b_stages;
           umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
+          if (dbg && b_it == 0) dbg[2] = clock64();
           const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
           for (int li = 0; li < ph.lin; ++li) {
             const TcSched s = ph.sched[li];
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const int as = a_it % a.a_stages;
             umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
             umma::tc_fence_after();
+            if (dbg && a_it == 0) dbg[3] = clock64();
             const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
             // first K chunk: the window's positions may differ in "already written", so issue one
             // MMA per position with its own accumulate flag; afterwards one windowed MMA.
@@ -228,6 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
       }
       umma::mma_commit(acc_full);
+      if (dbg) dbg[4] = clock64();
     }
   } else {
     // ===== epilogue: 8 warps; a thread owns one accumulator lane (trajectory row) and every other
@@ -243,6 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int gpt = a.ct / a.cg;                  // GroupNorm groups in this column tile (1 or 2)
     umma::mbar_wait(acc_full, 0);
     umma::tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
 
     float mean[2] = {0.0f, 0.0f}, rstd[2] = {1.0f, 1.0f};
     if (a.mode != TC_BIAS) {
@@ -292,73 +302,108 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       rstd[0] = rsqrtf((s2[0 * 128 + row_local] + s2[2 * 128 + row_local]) * inv_n + 1e-5f);
       rstd[1] = rsqrtf((s2[1 * 128 + row_local] + s2[3 * 128 + row_local]) * inv_n + 1e-5f);
     }
+    // Results are staged in shared memory (the operand stages are free once the accumulator is
+    // complete) and written out cooperatively so every store instruction covers whole sectors:
+    // a thread-per-row store pattern would touch 32 different 128-byte lines per instruction.
     const int kch_out = a.cout >> 5;
-    for (int u = half; u < n_units; u += 2) {
-      float v[16];
-      umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
-      const int lo = (u * 16) / a.ct;
-      const int c0 = (u * 16) % a.ct;
-      const int cglob = nt * a.ct + c0;          // first of 16 consecutive output channels
+    float* stg = reinterpret_cast<float*>(a_smem);
+    const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
+    const int plain_stride = N + 1;                // odd row stride: conflict-free column writes
+    for (int u0 = 0; u0 < n_units; u0 += a.epi_units) {
+      const int u1 = min(n_units, u0 + a.epi_units);
+      float* stg_lo = stg + (size_t)a.epi_units * 2048;
+      for (int u = u0 + half; u < u1; u += 2) {
+        float v[16];
+        umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
+        const int lo = (u * 16) / a.ct;
+        const int c0 = (u * 16) % a.ct;
+        const int cglob = nt * a.ct + c0;          // first of 16 consecutive output channels
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float y = v[i] + s_par[c0 + i];
-        if (a.mode != TC_BIAS) {
-          const int g = (gpt == 2 && i >= 8) ? 1 : 0;
-          y = (y - mean[g]) * rstd[g] * s_par[64 + c0 + i] + s_par[128 + c0 + i];
-          y = mish_fast(y) + s_par[192 + c0 + i];
+        for (int i = 0; i < 16; ++i) {
+          float y = v[i] + s_par[c0 + i];
+          if (a.mode != TC_BIAS) {
+            const bool g1 = (gpt == 2 && i >= 8);
+            y = (y - (g1 ? mean[1] : mean[0])) * (g1 ? rstd[1] : rstd[0]) * s_par[64 + c0 + i] + s_par[128 + c0 + i];
+            y = mish_fast(y) + s_par[192 + c0 + i];
+          }
+          v[i] = y;
         }
-        v[i] = y;
-      }
-      if (a.mode == TC_GN_RES_PW) {
-        float r[16];
-        umma::tmem_ld16(t_lane + a.ph[1].d_col + u * 16, r);
+        if (a.mode == TC_GN_RES_PW) {
+          float r[16];
+          umma::tmem_ld16(t_lane + a.ph[1].d_col + u * 16, r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
-      } else if (a.mode == TC_GN_RES_ID) {
-        // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
-        const int k = lo * a.res.C + cglob;
-        const size_t blk = ((size_t)rt * (a.lout * (a.res.C >> 5)) + (k >> 5)) * kTcBlock;
-        const int j0 = (k & 31) >> 2;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int off = tc_swz(row_local, j0 + m);
-          const float4 h = *reinterpret_cast<const float4*>(a.res.hi + blk + off);
-          float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.res.lo) l = *reinterpret_cast<const float4*>(a.res.lo + blk + off);
-          v[m * 4 + 0] += h.x + l.x;
-          v[m * 4 + 1] += h.y + l.y;
-          v[m * 4 + 2] += h.z + l.z;
-          v[m * 4 + 3] += h.w + l.w;
-        }
-      }
-      if (valid) {
-        if (a.out_hi) {
-          const int k = lo * a.cout + cglob;
-          const size_t blk = ((size_t)rt * (a.lout * kch_out) + (k >> 5)) * kTcBlock;
+          for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
+        } else if (a.mode == TC_GN_RES_ID) {
+          // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
+          const int k = lo * a.res.C + cglob;
+          const size_t blk = ((size_t)rt * (a.lout * (a.res.C >> 5)) + (k >> 5)) * kTcBlock;
           const int j0 = (k & 31) >> 2;
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int off = tc_swz(row_local, j0 + m);
+            const float4 h = *reinterpret_cast<const float4*>(a.res.hi + blk + off);
+            float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.res.lo) l = *reinterpret_cast<const float4*>(a.res.lo + blk + off);
+            v[m * 4 + 0] += h.x + l.x;
+            v[m * 4 + 1] += h.y + l.y;
+            v[m * 4 + 2] += h.z + l.z;
+            v[m * 4 + 3] += h.w + l.w;
+          }
+        }
+        if (a.out_hi) {
+          // staging tile of this unit: [128 rows][4 x 16 B], chunk m of row r at position m ^ ((r>>1)&3)
+          float* sh = stg + ((size_t)(u - u0) * 128 + row_local) * 16;
+          float* sl = stg_lo + ((size_t)(u - u0) * 128 + row_local) * 16;
+          const int sw = (row_local >> 1) & 3;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
             float4 h, l;
             if (a.out_lo) {
               h.x = umma::to_tf32(v[m * 4 + 0]); l.x = umma::to_tf32(v[m * 4 + 0] - h.x);
               h.y = umma::to_tf32(v[m * 4 + 1]); l.y = umma::to_tf32(v[m * 4 + 1] - h.y);
               h.z = umma::to_tf32(v[m * 4 + 2]); l.z = umma::to_tf32(v[m * 4 + 2] - h.z);
               h.w = umma::to_tf32(v[m * 4 + 3]); l.w = umma::to_tf32(v[m * 4 + 3] - h.w);
-              *reinterpret_cast<float4*>(a.out_lo + blk + off) = l;
+              *reinterpret_cast<float4*>(sl + ((m ^ sw) << 2)) = l;
             } else {
               h = make_float4(v[m * 4 + 0], v[m * 4 + 1], v[m * 4 + 2], v[m * 4 + 3]);
             }
-            *reinterpret_cast<float4*>(a.out_hi + blk + off) = h;
+            *reinterpret_cast<float4*>(sh + ((m ^ sw) << 2)) = h;
           }
-        }
-        if (a.out_plain) {
-          float* o = a.out_plain + ((size_t)row * a.cout + cglob) * a.lout + lo;
+        } else {
+          // plain [row][c][l] staging: this CTA's channels are one contiguous run per row
+          float* sp = stg + (size_t)row_local * plain_stride + (size_t)c0 * a.lout + lo;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[(size_t)i * a.lout] = v[i];
+          for (int i = 0; i < 16; ++i) sp[(size_t)i * a.lout] = v[i];
         }
       }
+      epi_barrier();
+      if (a.out_hi) {
+        const int items = (u1 - u0) * 512;          // (unit, row, 16-byte chunk)
+        for (int idx = et; idx < items; idx += 256) {
+          const int m = idx & 3, r = (idx >> 2) & 127, uu = idx >> 9;
+          if (rt * kTcRows + r >= a.rows) continue;
+          const int u = u0 + uu;
+          const int lo = (u * 16) / a.ct;
+          const int k = lo * a.cout + nt * a.ct + (u * 16) % a.ct;
+          const size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> 5)) * kTcBlock + tc_swz(r, ((k & 31) >> 2) + m);
+          const int src = (uu * 128 + r) * 16 + ((m ^ ((r >> 1) & 3)) << 2);
+          *reinterpret_cast<float4*>(a.out_hi + dst) = *reinterpret_cast<const float4*>(stg + src);
+          if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst) = *reinterpret_cast<const float4*>(stg_lo + src);
+        }
+      } else {
+        // all units of a plain-output layer fit one round (host guarantees it)
+        const int ew = et >> 5;
+        for (int r = ew; r < kTcRows; r += 8) {
+          const int grow = rt * kTcRows + r;
+          if (grow >= a.rows) break;
+          float* o = a.out_plain + ((size_t)grow * a.cout + (size_t)nt * a.ct) * a.lout;
+          const float* sp = stg + (size_t)r * plain_stride;
+          for (int e = lane; e < N; e += 32) o[e] = sp[e];
+        }
+      }
+      epi_barrier();
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     umma::tc_fence_before();
   }
   __syncthreads();
@@ -366,6 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     umma::tc_fence_after();
     umma::tmem_dealloc<512>(tmem_base);
   }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 // plain [rows][C][L] float32  ->  tiled hi/lo operand blocks (K order (l, c))

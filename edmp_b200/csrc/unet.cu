@@ -218,6 +218,7 @@ struct UNet {
   int precision = 0;
   bool tc = false;        // tensor-core path for the L <= 7 levels
   bool tc_split = false;  // 3xTF32 (hi/lo operands)
+  long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   int max_rows = 0;
   int n_launches = 0;
   std::vector<float*> dev_allocs;
@@ -422,7 +423,20 @@ struct Builder {
     ok = ok && t.a_stages >= 2;
     ly.kind = LAYER_TC;
     ly.tc_tiles = n_tiles;
-    ly.tc_smem = 1024 + t.a_stages * a_stage + t.b_stages * b_stage + 6144;
+    // epilogue staging reuses the operand stages; plain-output layers need the whole tile at once
+    size_t stage_total = t.a_stages * a_stage + t.b_stages * b_stage;
+    const int n_units = t.lout * t.ct / 16;
+    if (t.out_plain) {
+      const size_t need = (size_t)kTcRows * (t.lout * t.ct + 1) * sizeof(float);
+      stage_total = std::max(stage_total, need);
+      ok = ok && need <= budget;
+      t.epi_units = (n_units + 1) & ~1;
+    } else {
+      const int cap = (int)(stage_total / (16384 * (t.split ? 1 : 1)));   // hi + lo halves: 2 x 8 KB per unit
+      t.epi_units = std::max(2, std::min((n_units + 1) & ~1, cap & ~1));
+    }
+    t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
+    ly.tc_smem = 1024 + t.stage_bytes + 6144;
   }
 
   static TcOperand operand(const Act* a) {
@@ -739,6 +753,7 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     TcArgs a = ly.targs;
     a.rows = rows;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
+    a.dbg = u->dbg;
     dim3 grid((rows + kTcRows - 1) / kTcRows, ly.tc_tiles);
     conv_tc_kernel<<<grid, kTcThreads, ly.tc_smem, st>>>(a);
   } else {
@@ -794,6 +809,26 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
     macs[i] = i < n - 1 ? u->layers[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+// debug: run op `op` alone `iters` times and return the clock64 stamps of its CTAs ([ctas][8])
+int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st) {
+  EDMP_REQUIRE(op >= 0 && op < (int)u->layers.size() && u->layers[op].kind == LAYER_TC, "op is not a tensor-core layer");
+  Layer& ly = u->layers[op];
+  const int ctas = ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
+  EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
+  long long* d = nullptr;
+  EDMP_CK(cudaMalloc(&d, (size_t)ctas * 8 * sizeof(long long)));
+  EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 8 * sizeof(long long), st));
+  u->dbg = d;
+  const float* temb_row = u->temb;
+  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, st);
+  u->dbg = nullptr;
+  EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  EDMP_CK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  *n_ctas = ctas;
   return 0;
 }
 

@@ -77,6 +77,10 @@ int edmp_unet_read_activation(edmp_unet* u, const char* name, int rows, float* o
 int edmp_unet_profile(edmp_unet* u, const float* x_d, int t, int rows, int iters, float* ms_h,
                       double* macs_h, float* eps_d, void* stream);
 const char* edmp_unet_op_name(const edmp_unet* u, int i);
+/* debug: SM-clock stamps ([ctas][8]: entry, setup done, first weights, first activations, last MMA
+ * issued, accumulator ready, epilogue done, exit) of tensor-core op `op` run alone */
+int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas,
+                       void* stream);
 int edmp_unet_precision(const edmp_unet* u);
 /* number of kernels one forward launches (for bench.py's gpu_launches claim) */
 int edmp_unet_launches_per_forward(const edmp_unet* u);

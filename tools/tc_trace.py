@@ -1,0 +1,37 @@
+"""Per-CTA phase timing (SM clocks) of tensor-core ops: where does a conv_tc_kernel CTA spend time?"""
+import ctypes
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from edmp_b200 import TemporalUNet, _lib  # noqa: E402
+from oracle import weights  # noqa: E402
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1020
+prec = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
+dev = "cuda:0"
+m = TemporalUNet(os.path.join(tempfile.mkdtemp(), "m"), 7, 32, dev, dims=(32, 64, 128, 256, 512, 512), precision=prec)
+m.load_state_dict(weights.seeded_state_dict(0))
+x = torch.randn(rows, 7, 50, device=dev)
+m(x, 100)
+torch.cuda.synchronize()
+lib = _lib.load()
+h = m.engine(rows)
+n_ops = lib.edmp_unet_launches_per_forward(h)
+buf = np.zeros((4096, 8), dtype=np.int64)
+labels = ["setup", "wait W0", "wait A0", "mainloop issue", "acc ready", "epilogue", "teardown"]
+for i in range(n_ops - 1):
+    n = ctypes.c_int()
+    rc = lib.edmp_unet_tc_trace(h, i, rows, buf.ctypes.data_as(ctypes.c_void_p), 4096, ctypes.byref(n), None)
+    if rc != 0:
+        continue
+    t = buf[:n.value].astype(np.float64)
+    d = np.diff(t, axis=1)
+    total = t[:, 7] - t[:, 0]
+    print("%-36s ctas %3d  total %7.0f cyc (%5.1f us @1.9GHz) | " % (lib.edmp_unet_op_name(h, i).decode(), n.value,
+          total.mean(), total.mean() / 1900.0) + "  ".join("%s %6.0f" % (l, v) for l, v in zip(labels, d.mean(axis=0))))
