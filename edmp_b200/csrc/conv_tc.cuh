@@ -31,7 +31,9 @@ constexpr int kTcRows = 128;        // rows per CTA tile (UMMA M)
 constexpr int kTcChunk = 32;        // floats per K chunk (128 B)
 constexpr int kTcBlock = kTcRows * kTcChunk;   // floats per tiled operand block (16 KB)
 constexpr int kTcMaxLin = 13;
-constexpr int kTcThreads = 64 + 256;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int kTcEpiWarps = 16;             // epilogue warps: 4 per 32-lane TMEM quarter
+constexpr int kTcEpiThreads = kTcEpiWarps * 32;
+constexpr int kTcThreads = 64 + kTcEpiThreads;  // producer warp, MMA warp, epilogue warps
 
 struct TcOperand {      // tiled activation: blocks [row_tile][l * C/32 + c/32][128 x 32 swizzled]
   const float* hi;
@@ -90,7 +92,7 @@ __device__ __forceinline__ float mish_fast(float x) {
   return x > 20.0f ? x : x * __fdividef(n, n + 2.0f);
 }
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* b_empty = b_full + a.b_stages;
   uint64_t* acc_full = b_empty + a.b_stages;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
-  float* s_par = (float*)(tmem_slot + 2);   // bias | gamma | beta | temb | bres, 64 floats each
-  float* s_stat = s_par + 320;              // [pass 2][half 2][group 2][128 rows] partial GroupNorm sums
+  __shared__ __align__(16) float s_par[5 * 64];   // bias | gamma | beta | temb | bres for this column tile
+  __shared__ float s_stat[2 * 4 * 2 * 128];        // [pass][part][group][row] partial GroupNorm sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, nt = blockIdx.y;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   }
   if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
   if (warp >= 2) {
-    const int e = threadIdx.x - 64;   // 0..255
+    const int e = threadIdx.x - 64;
     if (e < a.ct) {
       const int c = nt * a.ct + e;
       s_par[e] = a.bias[c];
@@ -239,13 +241,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       if (dbg) dbg[4] = clock64();
     }
   } else {
-    // ===== epilogue: 8 warps; a thread owns one accumulator lane (trajectory row) and every other
-    // 16-column unit of it (two warps share each 32-lane TMEM quarter) =====
+    // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th
+    // 16-column unit of it (four warps share each 32-lane TMEM quarter) =====
+    constexpr int kParts = kTcEpiWarps / 4;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which half of the column units
+    const int half = (warp - 2) >> 2;             // which share of the column units (0..kParts-1)
     const int row_local = quarter * 32 + lane;
-    const int row = rt * kTcRows + row_local;
-    const bool valid = row < a.rows;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int N = a.lout * a.ct;
     const int n_units = N >> 4;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       // partial sums of the two column halves meet in shared memory
       const float inv_n = 1.0f / (float)(a.cg * a.lout);
       float s[2] = {0.0f, 0.0f};
-      for (int u = half; u < n_units; u += 2) {
+      for (int u = half; u < n_units; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int c0 = (u * 16) % a.ct;
@@ -275,10 +276,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       s_stat[(half * 2 + 0) * 128 + row_local] = s[0];
       s_stat[(half * 2 + 1) * 128 + row_local] = s[1];
       epi_barrier();
-      mean[0] = (s_stat[0 * 128 + row_local] + s_stat[2 * 128 + row_local]) * inv_n;
-      mean[1] = (s_stat[1 * 128 + row_local] + s_stat[3 * 128 + row_local]) * inv_n;
+      {
+        float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) { t0 += s_stat[(q * 2 + 0) * 128 + row_local]; t1 += s_stat[(q * 2 + 1) * 128 + row_local]; }
+        mean[0] = t0 * inv_n;
+        mean[1] = t1 * inv_n;
+      }
       float ss[2] = {0.0f, 0.0f};
-      for (int u = half; u < n_units; u += 2) {
+      for (int u = half; u < n_units; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int c0 = (u * 16) % a.ct;
@@ -295,24 +301,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           }
         }
       }
-      float* s2 = s_stat + 512;
+      float* s2 = s_stat + kParts * 2 * 128;
       s2[(half * 2 + 0) * 128 + row_local] = ss[0];
       s2[(half * 2 + 1) * 128 + row_local] = ss[1];
       epi_barrier();
-      rstd[0] = rsqrtf((s2[0 * 128 + row_local] + s2[2 * 128 + row_local]) * inv_n + 1e-5f);
-      rstd[1] = rsqrtf((s2[1 * 128 + row_local] + s2[3 * 128 + row_local]) * inv_n + 1e-5f);
+      {
+        float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) { t0 += s2[(q * 2 + 0) * 128 + row_local]; t1 += s2[(q * 2 + 1) * 128 + row_local]; }
+        rstd[0] = rsqrtf(t0 * inv_n + 1e-5f);
+        rstd[1] = rsqrtf(t1 * inv_n + 1e-5f);
+      }
     }
     // Results are staged in shared memory (the operand stages are free once the accumulator is
     // complete) and written out cooperatively so every store instruction covers whole sectors:
     // a thread-per-row store pattern would touch 32 different 128-byte lines per instruction.
     const int kch_out = a.cout >> 5;
     float* stg = reinterpret_cast<float*>(a_smem);
-    const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
+    const int et = threadIdx.x - 64;               // index among the epilogue threads
     const int plain_stride = N + 1;                // odd row stride: conflict-free column writes
     for (int u0 = 0; u0 < n_units; u0 += a.epi_units) {
       const int u1 = min(n_units, u0 + a.epi_units);
       float* stg_lo = stg + (size_t)a.epi_units * 2048;
-      for (int u = u0 + half; u < u1; u += 2) {
+      for (int u = u0 + half; u < u1; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int lo = (u * 16) / a.ct;
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       epi_barrier();
       if (a.out_hi) {
         const int items = (u1 - u0) * 512;          // (unit, row, 16-byte chunk)
-        for (int idx = et; idx < items; idx += 256) {
+        for (int idx = et; idx < items; idx += kTcEpiThreads) {
           const int m = idx & 3, r = (idx >> 2) & 127, uu = idx >> 9;
           if (rt * kTcRows + r >= a.rows) continue;
           const int u = u0 + uu;
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       } else {
         // all units of a plain-output layer fit one round (host guarantees it)
         const int ew = et >> 5;
-        for (int r = ew; r < kTcRows; r += 8) {
+        for (int r = ew; r < kTcRows; r += kTcEpiWarps) {
           const int grow = rt * kTcRows + r;
           if (grow >= a.rows) break;
           float* o = a.out_plain + ((size_t)grow * a.cout + (size_t)nt * a.ct) * a.lout;

@@ -416,7 +416,7 @@ struct Builder {
     if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
     const size_t a_stage = (size_t)kTcBlock * 4 * nparts;
     const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
-    const size_t budget = 232448 - 1024 - 6144;   // dynamic smem limit - alignment slack - barriers/params/stats
+    const size_t budget = 232448 - 1024 - 1024 - 10240;   // dynamic limit - alignment slack - barriers - static smem
     t.b_stages = (2 * b_stage + 2 * a_stage <= budget) ? 2 : 1;
     size_t rest = budget - t.b_stages * b_stage;
     t.a_stages = (int)std::min<size_t>(4, rest / a_stage);
@@ -430,13 +430,13 @@ struct Builder {
       const size_t need = (size_t)kTcRows * (t.lout * t.ct + 1) * sizeof(float);
       stage_total = std::max(stage_total, need);
       ok = ok && need <= budget;
-      t.epi_units = (n_units + 1) & ~1;
+      t.epi_units = (n_units + 3) & ~3;
     } else {
       const int cap = (int)(stage_total / (16384 * (t.split ? 1 : 1)));   // hi + lo halves: 2 x 8 KB per unit
-      t.epi_units = std::max(2, std::min((n_units + 1) & ~1, cap & ~1));
+      t.epi_units = std::max(4, std::min((n_units + 3) & ~3, cap & ~3));
     }
     t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
-    ly.tc_smem = 1024 + t.stage_bytes + 6144;
+    ly.tc_smem = 1024 + t.stage_bytes + 1024;
   }
 
   static TcOperand operand(const Act* a) {
@@ -639,7 +639,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   if (u->tc) {
     static bool attr_set = false;
     if (!attr_set) {
-      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       attr_set = true;
     }
   }
