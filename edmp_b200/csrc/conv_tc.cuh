@@ -122,8 +122,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, 1); }
+    // one arrival per producer thread on the "full" barriers (hi and lo parts have their own thread)
+    for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, nparts); umma::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, nparts); umma::mbar_init(b_empty + i, 1); }
     umma::mbar_init(acc_full, 1);
     umma::fence_barrier_init();
   }
@@ -145,44 +146,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-  if (warp == 0) {
-    // ===== producer: bulk async copies of ready-made operand tiles =====
-    if (lane == 0) {
-      int a_it = 0, b_it = 0;
-      for (int p = 0; p < a.n_phases; ++p) {
-        const TcPhase& ph = a.ph[p];
-        const int ka = ph.a.C >> 5, kb = ph.b.C >> 5;
-        const int wtile_floats = ph.slots * a.ct * kTcChunk;
-        for (int cc = 0; cc < ka + kb; ++cc) {
-          {
-            const int bs = b_it % a.b_stages;
-            umma::mbar_wait(b_empty + bs, ((b_it / a.b_stages) & 1) ^ 1);
-            const uint32_t bytes = (uint32_t)wtile_floats * 4u;
-            umma::mbar_arrive_expect_tx(b_full + bs, bytes * nparts);
-            const size_t woff = ((size_t)nt * (ka + kb) + cc) * wtile_floats;
-            uint8_t* dst = b_smem + bs * b_stage_bytes;
-            umma::bulk_g2s(dst, ph.w_hi + woff, bytes, b_full + bs);
-            if (a.split) umma::bulk_g2s(dst + b_part_bytes, ph.w_lo + woff, bytes, b_full + bs);
-            ++b_it;
-          }
+  // ===== producers: bulk async copies of ready-made operand tiles.  One thread can keep only ~2
+  // bulk copies in flight (~20 B/cycle), separate threads scale linearly (tools/micro/bulk_bw.cu), so
+  // the activation-hi, activation-lo, weight-hi and weight-lo streams each get their own thread:
+  // lane 0 of warp 0 and of the first three epilogue warps (idle until the accumulator is ready).
+  int prod_kind = -1;   // 0: A hi, 1: A lo, 2: B hi, 3: B lo
+  if (lane == 0) {
+    if (warp == 0) prod_kind = 0;
+    else if (warp == 2 && a.split) prod_kind = 1;
+    else if (warp == 3) prod_kind = 2;
+    else if (warp == 4 && a.split) prod_kind = 3;
+  }
+  if (prod_kind >= 0) {
+    const bool is_lo = prod_kind & 1;
+    int a_it = 0, b_it = 0;
+    for (int p = 0; p < a.n_phases; ++p) {
+      const TcPhase& ph = a.ph[p];
+      const int ka = ph.a.C >> 5, kb = ph.b.C >> 5;
+      const int wtile_floats = ph.slots * a.ct * kTcChunk;
+      for (int cc = 0; cc < ka + kb; ++cc) {
+        if (prod_kind >= 2) {
+          const int bs = b_it % a.b_stages;
+          umma::mbar_wait(b_empty + bs, ((b_it / a.b_stages) & 1) ^ 1);
+          const uint32_t bytes = (uint32_t)wtile_floats * 4u;
+          umma::mbar_arrive_expect_tx(b_full + bs, bytes);
+          const size_t woff = ((size_t)nt * (ka + kb) + cc) * wtile_floats;
+          uint8_t* dst = b_smem + bs * b_stage_bytes + (is_lo ? b_part_bytes : 0);
+          umma::bulk_g2s(dst, (is_lo ? ph.w_lo : ph.w_hi) + woff, bytes, b_full + bs);
+          ++b_it;
+        } else {
           for (int li = 0; li < ph.lin; ++li) {
             if (ph.sched[li].n_slots == 0) continue;
             const int as = a_it % a.a_stages;
             umma::mbar_wait(a_empty + as, ((a_it / a.a_stages) & 1) ^ 1);
-            umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
+            umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)kTcBlock * 4u);
             const bool first = cc < ka;
             const TcOperand& op = first ? ph.a : ph.b;
             const int c2 = first ? cc : cc - ka;
-            uint8_t* dst = a_smem + as * a_stage_bytes;
-            umma::bulk_g2s(dst, tc_block(op.hi, op.C, ph.lin, rt, li, c2), kTcBlock * 4, a_full + as);
-            if (a.split)
-              umma::bulk_g2s(dst + kTcBlock * 4, tc_block(op.lo, op.C, ph.lin, rt, li, c2), kTcBlock * 4,
-                             a_full + as);
+            uint8_t* dst = a_smem + as * a_stage_bytes + (is_lo ? kTcBlock * 4 : 0);
+            umma::bulk_g2s(dst, tc_block(is_lo ? op.lo : op.hi, op.C, ph.lin, rt, li, c2), kTcBlock * 4, a_full + as);
             ++a_it;
           }
         }
       }
     }
+  }
+  if (warp == 0) {
+    // producer warp: nothing else to do
   } else if (warp == 1) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (lane == 0) {
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int n_units = N >> 4;
     const int gpt = a.ct / a.cg;                  // GroupNorm groups in this column tile (1 or 2)
     umma::mbar_wait(acc_full, 0);
+    __syncwarp();
     umma::tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
 
@@ -323,12 +334,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     for (int u0 = 0; u0 < n_units; u0 += a.epi_units) {
       const int u1 = min(n_units, u0 + a.epi_units);
       float* stg_lo = stg + (size_t)a.epi_units * 2048;
+      float* stg_res = stg + (size_t)a.epi_units * 4096;
+      if (a.mode == TC_GN_RES_ID) {
+        // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input, fetched
+        // with sector-coalesced loads into the staging area (same tile shape as the output)
+        const int items = (u1 - u0) * 512;
+        const int kch_res = a.res.C >> 5;
+        for (int idx = et; idx < items; idx += kTcEpiThreads) {
+          const int m = idx & 3, r = (idx >> 2) & 127, uu = idx >> 9;
+          const int u = u0 + uu;
+          const int lo = (u * 16) / a.ct;
+          const int k = lo * a.res.C + nt * a.ct + (u * 16) % a.ct;
+          const size_t src = ((size_t)rt * (a.lout * kch_res) + (k >> 5)) * kTcBlock + tc_swz(r, ((k & 31) >> 2) + m);
+          float4 h = *reinterpret_cast<const float4*>(a.res.hi + src);
+          if (a.res.lo) {
+            const float4 l = *reinterpret_cast<const float4*>(a.res.lo + src);
+            h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+          }
+          *reinterpret_cast<float4*>(stg_res + (uu * 128 + r) * 16 + ((m ^ ((r >> 1) & 3)) << 2)) = h;
+        }
+        epi_barrier();
+      }
       for (int u = u0 + half; u < u1; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int lo = (u * 16) / a.ct;
         const int c0 = (u * 16) % a.ct;
-        const int cglob = nt * a.ct + c0;          // first of 16 consecutive output channels
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float y = v[i] + s_par[c0 + i];
@@ -345,20 +376,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
         } else if (a.mode == TC_GN_RES_ID) {
-          // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
-          const int k = lo * a.res.C + cglob;
-          const size_t blk = ((size_t)rt * (a.lout * (a.res.C >> 5)) + (k >> 5)) * kTcBlock;
-          const int j0 = (k & 31) >> 2;
+          const float* sr = stg_res + ((size_t)(u - u0) * 128 + row_local) * 16;
+          const int sw = (row_local >> 1) & 3;
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
-            const int off = tc_swz(row_local, j0 + m);
-            const float4 h = *reinterpret_cast<const float4*>(a.res.hi + blk + off);
-            float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.res.lo) l = *reinterpret_cast<const float4*>(a.res.lo + blk + off);
-            v[m * 4 + 0] += h.x + l.x;
-            v[m * 4 + 1] += h.y + l.y;
-            v[m * 4 + 2] += h.z + l.z;
-            v[m * 4 + 3] += h.w + l.w;
+            const float4 h = *reinterpret_cast<const float4*>(sr + ((m ^ sw) << 2));
+            v[m * 4 + 0] += h.x;
+            v[m * 4 + 1] += h.y;
+            v[m * 4 + 2] += h.z;
+            v[m * 4 + 3] += h.w;
           }
         }
         if (a.out_hi) {

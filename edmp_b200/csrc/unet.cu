@@ -432,7 +432,8 @@ struct Builder {
       ok = ok && need <= budget;
       t.epi_units = (n_units + 3) & ~3;
     } else {
-      const int cap = (int)(stage_total / (16384 * (t.split ? 1 : 1)));   // hi + lo halves: 2 x 8 KB per unit
+      // per 16-column unit: 8 KB hi + 8 KB lo output staging (+ 8 KB residual staging)
+      const int cap = (int)(stage_total / (t.mode == TC_GN_RES_ID ? 24576 : 16384));
       t.epi_units = std::max(4, std::min((n_units + 3) & ~3, cap & ~3));
     }
     t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
