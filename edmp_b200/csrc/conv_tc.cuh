@@ -194,9 +194,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   if (warp == 0) {
     // producer warp: nothing else to do
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread drives the tensor core =====
-    if (lane == 0) {
+    // ===== MMA issuer.  The whole warp walks the schedule so that every descriptor is computed on
+    // the uniform datapath; only the tcgen05 instructions themselves are issued by one elected lane
+    // (a divergent single-lane loop costs a ~14-instruction R2UR "waterfall" per MMA). =====
+    {
       int a_it = 0, b_it = 0;
+      const uint64_t desc0 = umma::make_desc_sw128(0);
       for (int p = 0; p < a.n_phases; ++p) {
         const TcPhase& ph = a.ph[p];
         const int kc_total = (ph.a.C + ph.b.C) >> 5;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         for (int cc = 0; cc < kc_total; ++cc) {
           const int bs = b_it % a.b_stages;
           umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
-          if (dbg && b_it == 0) dbg[2] = clock64();
+          if (dbg && b_it == 0 && lane == 0) dbg[2] = clock64();
           const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
           for (int li = 0; li < ph.lin; ++li) {
             const TcSched s = ph.sched[li];
@@ -212,8 +215,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const int as = a_it % a.a_stages;
             umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
             umma::tc_fence_after();
-            if (dbg && a_it == 0) dbg[3] = clock64();
+            if (dbg && a_it == 0 && lane == 0) dbg[3] = clock64();
             const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
+            const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+            const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlock * 4) & 0x3FFFF) >> 4);
             // first K chunk: the window's positions may differ in "already written", so issue one
             // MMA per position with its own accumulate flag; afterwards one windowed MMA.
             const int n_issue = (cc == 0) ? s.n_slots : 1;
@@ -224,31 +229,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               const uint32_t acc0 = (cc == 0) ? ((touched >> lo) & 1u) : 1u;
               const uint32_t d = tmem_base + (uint32_t)(ph.d_col + lo * a.ct);
               const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + q) * a.ct * 128);
+              const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
+              const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_part_bytes) & 0x3FFFF) >> 4);
+              if (umma::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t da_hi = umma::make_desc_sw128(a_base + ks * 32);
-                const uint64_t db_hi = umma::make_desc_sw128(b_off + ks * 32);
-                if (a.split) {
-                  const uint64_t da_lo = umma::make_desc_sw128(a_base + kTcBlock * 4 + ks * 32);
-                  const uint64_t db_lo = umma::make_desc_sw128(b_off + b_part_bytes + ks * 32);
-                  umma::mma_tf32(d, da_lo, db_hi, idesc, (acc0 | (uint32_t)(ks > 0)));
-                  umma::mma_tf32(d, da_hi, db_lo, idesc, 1u);
-                  umma::mma_tf32(d, da_hi, db_hi, idesc, 1u);
-                } else {
-                  umma::mma_tf32(d, da_hi, db_hi, idesc, (acc0 | (uint32_t)(ks > 0)));
+                for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom: +2 in the address field
+                  if (a.split) {
+                    umma::mma_tf32(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, (acc0 | (uint32_t)(ks > 0)));
+                    umma::mma_tf32(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                  } else {
+                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, (acc0 | (uint32_t)(ks > 0)));
+                  }
                 }
               }
+              __syncwarp();
               if (cc == 0) touched |= 1u << lo;
             }
-            umma::mma_commit(a_empty + as);   // frees the A stage once these MMAs have read it
+            if (umma::elect_one()) umma::mma_commit(a_empty + as);   // frees the A stage once these MMAs have read it
+            __syncwarp();
             ++a_it;
           }
-          umma::mma_commit(b_empty + bs);
+          if (umma::elect_one()) umma::mma_commit(b_empty + bs);
+          __syncwarp();
           ++b_it;
         }
       }
-      umma::mma_commit(acc_full);
-      if (dbg) dbg[4] = clock64();
+      if (umma::elect_one()) umma::mma_commit(acc_full);
+      __syncwarp();
+      if (dbg && lane == 0) dbg[4] = clock64();
     }
   } else {
     // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th

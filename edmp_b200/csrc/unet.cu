@@ -433,7 +433,9 @@ struct Builder {
       t.epi_units = (n_units + 3) & ~3;
     } else {
       // per 16-column unit: 8 KB hi + 8 KB lo output staging (+ 8 KB residual staging)
-      const int cap = (int)(stage_total / (t.mode == TC_GN_RES_ID ? 24576 : 16384));
+      const size_t per_unit = t.mode == TC_GN_RES_ID ? 24576 : 16384;
+      stage_total = std::max(stage_total, 4 * per_unit);
+      const int cap = (int)(stage_total / per_unit);
       t.epi_units = std::max(4, std::min((n_units + 3) & ~3, cap & ~3));
     }
     t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
