@@ -1,43 +1,47 @@
-// Tensor-core (tcgen05 + TMEM) convolution kernel for the short-horizon levels of the TemporalUNet
-// (L <= 7: 87 % of the network's multiply-accumulates).
+// Tensor-core (tcgen05 + TMEM) convolution kernel for the TemporalUNet levels with horizon <= 13
+// (94 % of the network's multiply-accumulates).
 //
 // GEMM view ("rows as M"):  D[row, (l_out, c_out)] = sum_{(l_in, c_in)} X[row, (l_in, c_in)] * W
 //   * M = 128 trajectory rows per CTA (UMMA_M = 128, cta_group::1), accumulator in TMEM;
-//   * the K axis is ordered (l_in, c_in) and cut into 32-float (128 B) chunks, so one K chunk is
-//     one input position l_in and 32 input channels;
+//   * the K axis is ordered (l_in, c_in) and cut into 128-byte chunks (32 tf32 or 64 bf16 input
+//     channels of ONE input position l_in);
 //   * the N axis of a CTA is ordered (l_out, channel-in-tile); a K chunk at l_in only touches the
 //     output positions within the filter's reach, i.e. a contiguous column window of the
 //     accumulator, so each chunk is ONE windowed tcgen05.mma (N_w = #positions x channels) and no
 //     zero-padding tap is ever multiplied (exactly the non-padding MACs);
 //   * operands are pre-tiled in global memory as ready-made UMMA shared-memory images
-//     (128 rows x 128 B, SWIZZLE_128B, K-major): the producer warp moves them with 1-D bulk async
+//     (128 rows x 128 B, SWIZZLE_128B, K-major): producer threads move them with 1-D bulk async
 //     copies (TMA engine) signalled on mbarriers -- no tensor maps needed;
-//   * fp32 fidelity: every operand exists as a TF32 "hi" part and a TF32 "lo" remainder and each
-//     product is three MMAs (hi*hi + lo*hi + hi*lo), error ~2^-22 ("3xTF32");
-//   * warp roles: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//     warps 2..5 = epilogue (TMEM -> registers; GroupNorm over the CTA's own columns: a thread owns
-//     one row, so the group statistics are a private serial reduction; Mish; time embedding /
-//     residual; TF32 hi/lo split; stores in the tiled format the next layer consumes).
+//   * fp32 fidelity: every operand exists as a "hi" part and a "lo" remainder (TF32 or BF16) and
+//     each product is three MMAs (lo*hi + hi*lo + hi*hi): "3xTF32" (~2^-22 operand error) or
+//     "3xBF16" (~2^-17).  The single-pass modes use the hi part only;
+//   * warp roles: warp 0 + lane 0 of three epilogue warps = bulk-copy producers (one thread per
+//     operand stream), warp 1 = TMEM allocator + MMA issuer (warp-uniform schedule walk, one
+//     elected lane issues), warps 2..17 = epilogue (TMEM -> registers; GroupNorm over the CTA's
+//     own columns: a thread owns one row, so group statistics are private serial reductions that
+//     meet in shared memory; Mish; time embedding / residual; hi/lo split; results staged in shared
+//     memory and written out in the tiled format the next layer consumes).
 //
 // Reference ops covered: Conv1dBlock (blocks.py:13-34), ResidualConvolutionBlock (:137-166) incl.
 // the 1x1 residual conv (second accumulator), stride-2 Conv1d (:211), ConvTranspose1d (:249).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace edmp {
 
-constexpr int kTcRows = 128;        // rows per CTA tile (UMMA M)
-constexpr int kTcChunk = 32;        // floats per K chunk (128 B)
-constexpr int kTcBlock = kTcRows * kTcChunk;   // floats per tiled operand block (16 KB)
+constexpr int kTcRows = 128;                 // rows per CTA tile (UMMA M)
+constexpr int kTcBlockBytes = kTcRows * 128; // bytes of one tiled operand block (128 rows x 128 B)
 constexpr int kTcMaxLin = 13;
-constexpr int kTcEpiWarps = 16;             // epilogue warps: 4 per 32-lane TMEM quarter
+constexpr int kTcEpiWarps = 16;              // epilogue warps: 4 per 32-lane TMEM quarter
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
 constexpr int kTcThreads = 64 + kTcEpiThreads;  // producer warp, MMA warp, epilogue warps
 
-struct TcOperand {      // tiled activation: blocks [row_tile][l * C/32 + c/32][128 x 32 swizzled]
-  const float* hi;
-  const float* lo;
+struct TcOperand {      // tiled activation: blocks [row_tile][l * C/cpc + c/cpc][128 rows x 128 B swizzled]
+  const void* hi;
+  const void* lo;
   int C;
 };
 
@@ -50,8 +54,8 @@ struct TcSched {        // what one K chunk at input position l_in contributes t
 
 struct TcPhase {
   TcOperand a, b;       // b.C == 0 unless the input is a skip concat (blocks.py:253)
-  const float* w_hi;    // packed weights [n_tile][c_chunk][slots * ct rows][32] swizzled
-  const float* w_lo;
+  const void* w_hi;     // packed weights [n_tile][c_chunk][slots * ct rows][128 B] swizzled
+  const void* w_lo;
   int lin;              // input positions
   int slots;            // slots stored per weight tile
   int d_col;            // accumulator column base
@@ -66,25 +70,38 @@ struct TcArgs {
   int rows, lout, ct, cout;     // ct = channels per CTA column tile; N = lout * ct
   int cg;                       // channels per GroupNorm group (ct / cg groups per column tile, 1 or 2)
   int mode;
-  int split;                    // 1 = 3xTF32 (hi/lo), 0 = single TF32 pass
+  int split;                    // 1 = three-MMA hi/lo split, 0 = single pass
   int a_stages, b_stages;
-  int epi_units;                // 16-column units staged in shared memory per epilogue round (even)
+  int epi_units;                // 16-column units staged in shared memory per epilogue round (multiple of 4)
   int stage_bytes;              // bytes reserved for operand stages / epilogue staging (barriers follow)
   const float *bias, *gamma, *beta, *temb, *bres;
   TcOperand res;                // identity residual source (tiled)
-  float *out_hi, *out_lo;       // tiled output [row_tile][l*cout/32 + c/32][...], may be null
+  void *out_hi, *out_lo;        // tiled output, may be null
   float* out_plain;             // plain [rows][cout][lout], may be null
-  long long* dbg;               // optional [ctas][8] clock64 stamps (tools/tc_debug.py), normally null
+  long long* dbg;               // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
 };
 
-__device__ __forceinline__ const float* tc_block(const float* base, int C, int lin, int rt, int li, int cc) {
-  return base + ((size_t)rt * (lin * (C >> 5)) + (size_t)li * (C >> 5) + cc) * kTcBlock;
+// Element-type traits: TF32 operands are 4-byte floats (32 per 128-byte row), BF16 2-byte (64 per row)
+template <bool BF16> struct TcElem;
+template <> struct TcElem<false> {
+  static constexpr int kCpc = 32;      // channels per K chunk
+  static constexpr int kShift = 5;
+  static constexpr int kFmt = 2;       // UMMA a/b format TF32
+  static constexpr int kUnitChunks = 4;  // 16-byte chunks that 16 channels occupy
+};
+template <> struct TcElem<true> {
+  static constexpr int kCpc = 64;
+  static constexpr int kShift = 6;
+  static constexpr int kFmt = 1;       // BF16
+  static constexpr int kUnitChunks = 2;
+};
+
+// byte offset of 16-byte chunk `chunk16` of row `row_local` inside a tiled block
+__device__ __forceinline__ int tc_swz_bytes(int row_local, int chunk16) {
+  return row_local * 128 + ((chunk16 ^ (row_local & 7)) << 4);
 }
 
-// element (row_local, k) of a tiled block lives at float offset row*32 + ((k/4) ^ (row & 7))*4 + k%4
-__device__ __forceinline__ int tc_swz(int row_local, int chunk16) { return row_local * 32 + ((chunk16 ^ (row_local & 7)) << 2); }
-
-// Mish with hardware exp2 / reciprocal approximations (rel. error ~1e-6, below the 3xTF32
+// Mish with hardware exp2 / reciprocal approximations (rel. error ~1e-6, below the split-MMA
 // accumulation error); the CUDA-core path keeps the accurate version.
 __device__ __forceinline__ float mish_fast(float x) {
   const float e = __expf(fminf(x, 20.0f));
@@ -94,12 +111,70 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// split 16 fp32 values into hi/lo parts in the operand element type; writes kUnitChunks 16-byte chunks each
+template <bool BF16>
+__device__ __forceinline__ void tc_split_store(const float (&v)[16], bool want_lo, uint4* hi, uint4* lo) {
+  if (BF16) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = v[m * 8 + 2 * e], x1 = v[m * 8 + 2 * e + 1];
+        h[e] = pack_bf16x2(x0, x1);
+        l[e] = want_lo ? pack_bf16x2(x0 - bf16_lo_f(h[e]), x1 - bf16_hi_f(h[e])) : 0u;
+      }
+      hi[m] = make_uint4(h[0], h[1], h[2], h[3]);
+      lo[m] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x = v[m * 4 + e];
+        h[e] = want_lo ? umma::to_tf32(x) : x;
+        l[e] = want_lo ? umma::to_tf32(x - h[e]) : 0.0f;
+      }
+      hi[m] = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]), __float_as_uint(h[3]));
+      lo[m] = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
+    }
+  }
+}
+
+// sum of the hi and lo 16-byte chunks as fp32 values (4 for TF32, 8 for BF16)
+template <bool BF16>
+__device__ __forceinline__ void tc_chunk_sum(const uint4& h, const uint4& l, bool has_lo, float* out) {
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+  if (BF16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      out[2 * e] = bf16_lo_f(hh[e]) + (has_lo ? bf16_lo_f(ll[e]) : 0.0f);
+      out[2 * e + 1] = bf16_hi_f(hh[e]) + (has_lo ? bf16_hi_f(ll[e]) : 0.0f);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = __uint_as_float(hh[e]) + (has_lo ? __uint_as_float(ll[e]) : 0.0f);
+  }
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  using E = TcElem<BF16>;
+  constexpr int UC = E::kUnitChunks;           // 16-byte chunks per (row, 16-channel unit)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers][params]
+  // carve: [A stages][B stages] ... [barriers]; statically: parameters and GroupNorm partials
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nparts = a.split ? 2 : 1;
-  const int a_stage_bytes = kTcBlock * 4 * nparts;
+  const int a_stage_bytes = kTcBlockBytes * nparts;
   int max_slots = a.ph[0].slots;
   if (a.n_phases > 1 && a.ph[1].slots > max_slots) max_slots = a.ph[1].slots;
   const int b_part_bytes = max_slots * a.ct * 128;
@@ -162,109 +237,122 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     int a_it = 0, b_it = 0;
     for (int p = 0; p < a.n_phases; ++p) {
       const TcPhase& ph = a.ph[p];
-      const int ka = ph.a.C >> 5, kb = ph.b.C >> 5;
-      const int wtile_floats = ph.slots * a.ct * kTcChunk;
+      const int ka = ph.a.C >> E::kShift, kb = ph.b.C >> E::kShift;
+      const uint32_t wtile_bytes = (uint32_t)ph.slots * a.ct * 128u;
       for (int cc = 0; cc < ka + kb; ++cc) {
         if (prod_kind >= 2) {
           const int bs = b_it % a.b_stages;
           umma::mbar_wait(b_empty + bs, ((b_it / a.b_stages) & 1) ^ 1);
-          const uint32_t bytes = (uint32_t)wtile_floats * 4u;
-          umma::mbar_arrive_expect_tx(b_full + bs, bytes);
-          const size_t woff = ((size_t)nt * (ka + kb) + cc) * wtile_floats;
+          umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes);
+          const size_t woff = ((size_t)nt * (ka + kb) + cc) * wtile_bytes;
           uint8_t* dst = b_smem + bs * b_stage_bytes + (is_lo ? b_part_bytes : 0);
-          umma::bulk_g2s(dst, (is_lo ? ph.w_lo : ph.w_hi) + woff, bytes, b_full + bs);
+          umma::bulk_g2s(dst, (const uint8_t*)(is_lo ? ph.w_lo : ph.w_hi) + woff, wtile_bytes, b_full + bs);
           ++b_it;
         } else {
           for (int li = 0; li < ph.lin; ++li) {
             if (ph.sched[li].n_slots == 0) continue;
             const int as = a_it % a.a_stages;
             umma::mbar_wait(a_empty + as, ((a_it / a.a_stages) & 1) ^ 1);
-            umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)kTcBlock * 4u);
+            umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)kTcBlockBytes);
             const bool first = cc < ka;
             const TcOperand& op = first ? ph.a : ph.b;
             const int c2 = first ? cc : cc - ka;
-            uint8_t* dst = a_smem + as * a_stage_bytes + (is_lo ? kTcBlock * 4 : 0);
-            umma::bulk_g2s(dst, tc_block(is_lo ? op.lo : op.hi, op.C, ph.lin, rt, li, c2), kTcBlock * 4, a_full + as);
+            const int kop = op.C >> E::kShift;
+            const size_t blk = ((size_t)rt * (ph.lin * kop) + (size_t)li * kop + c2) * kTcBlockBytes;
+            uint8_t* dst = a_smem + as * a_stage_bytes + (is_lo ? kTcBlockBytes : 0);
+            umma::bulk_g2s(dst, (const uint8_t*)(is_lo ? op.lo : op.hi) + blk, kTcBlockBytes, a_full + as);
             ++a_it;
           }
         }
       }
     }
   }
+
   if (warp == 0) {
     // producer warp: nothing else to do
   } else if (warp == 1) {
     // ===== MMA issuer.  The whole warp walks the schedule so that every descriptor is computed on
     // the uniform datapath; only the tcgen05 instructions themselves are issued by one elected lane
-    // (a divergent single-lane loop costs a ~14-instruction R2UR "waterfall" per MMA). =====
-    {
-      int a_it = 0, b_it = 0;
-      const uint64_t desc0 = umma::make_desc_sw128(0);
-      for (int p = 0; p < a.n_phases; ++p) {
-        const TcPhase& ph = a.ph[p];
-        const int kc_total = (ph.a.C + ph.b.C) >> 5;
-        uint32_t touched = 0;   // output positions whose accumulator columns already hold a partial sum
-        for (int cc = 0; cc < kc_total; ++cc) {
-          const int bs = b_it % a.b_stages;
-          umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
-          if (dbg && b_it == 0 && lane == 0) dbg[2] = clock64();
-          const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
-          for (int li = 0; li < ph.lin; ++li) {
-            const TcSched s = ph.sched[li];
-            if (s.n_slots == 0) continue;
-            const int as = a_it % a.a_stages;
-            umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
-            umma::tc_fence_after();
-            if (dbg && a_it == 0 && lane == 0) dbg[3] = clock64();
-            const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
-            const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
-            const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlock * 4) & 0x3FFFF) >> 4);
-            // first K chunk: the window's positions may differ in "already written", so issue one
-            // MMA per position with its own accumulate flag; afterwards one windowed MMA.
-            const int n_issue = (cc == 0) ? s.n_slots : 1;
-            const int n_cols = ((cc == 0) ? 1 : s.n_slots) * a.ct;
-            const uint32_t idesc = umma::make_idesc(2, kTcRows, n_cols);
-            for (int q = 0; q < n_issue; ++q) {
-              const int lo = s.lo_begin + q;
-              const uint32_t acc0 = (cc == 0) ? ((touched >> lo) & 1u) : 1u;
-              const uint32_t d = tmem_base + (uint32_t)(ph.d_col + lo * a.ct);
-              const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + q) * a.ct * 128);
-              const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
-              const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_part_bytes) & 0x3FFFF) >> 4);
-              if (umma::elect_one()) {
+    // (a divergent single-lane loop costs a ~14-instruction R2UR "waterfall" per MMA).  Measured
+    // cost of one M=128 SS-mode MMA is ~40 + N/2 cycles for tf32 (K=8) and bf16 (K=16) alike
+    // (tools/micro/mma_rate.cu), so bf16 operands halve the mainloop. =====
+    int a_it = 0, b_it = 0;
+    const uint64_t desc0 = umma::make_desc_sw128(0);
+    for (int p = 0; p < a.n_phases; ++p) {
+      const TcPhase& ph = a.ph[p];
+      const int kc_total = (ph.a.C + ph.b.C) >> E::kShift;
+      uint32_t touched = 0;   // output positions whose accumulator columns already hold a partial sum
+      for (int cc = 0; cc < kc_total; ++cc) {
+        const int bs = b_it % a.b_stages;
+        umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
+        if (dbg && b_it == 0 && lane == 0) dbg[2] = clock64();
+        const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
+        for (int li = 0; li < ph.lin; ++li) {
+          const TcSched s = ph.sched[li];
+          if (s.n_slots == 0) continue;
+          const int as = a_it % a.a_stages;
+          umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
+          umma::tc_fence_after();
+          if (dbg && a_it == 0 && lane == 0) dbg[3] = clock64();
+          const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
+          const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+          const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+          // first K chunk: the window's positions may differ in "already written", so issue one
+          // MMA per position with its own accumulate flag; afterwards one windowed MMA.
+          const int n_issue = (cc == 0) ? s.n_slots : 1;
+          const int n_cols = ((cc == 0) ? 1 : s.n_slots) * a.ct;
+          const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows, n_cols);
+          for (int q = 0; q < n_issue; ++q) {
+            const int lo = s.lo_begin + q;
+            const uint32_t acc0 = (cc == 0) ? ((touched >> lo) & 1u) : 1u;
+            const uint32_t d = tmem_base + (uint32_t)(ph.d_col + lo * a.ct);
+            const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + q) * a.ct * 128);
+            const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
+            const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_part_bytes) & 0x3FFFF) >> 4);
+            if (umma::elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom: +2 in the address field
+              for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom: +2 in the address field
+                const uint32_t acc = acc0 | (uint32_t)(ks > 0);
+                if (BF16) {
                   if (a.split) {
-                    umma::mma_tf32(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, (acc0 | (uint32_t)(ks > 0)));
+                    umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                    umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                    umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                  } else {
+                    umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                  }
+                } else {
+                  if (a.split) {
+                    umma::mma_tf32(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
                     umma::mma_tf32(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
                     umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
                   } else {
-                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, (acc0 | (uint32_t)(ks > 0)));
+                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
                   }
                 }
               }
-              __syncwarp();
-              if (cc == 0) touched |= 1u << lo;
             }
-            if (umma::elect_one()) umma::mma_commit(a_empty + as);   // frees the A stage once these MMAs have read it
             __syncwarp();
-            ++a_it;
+            if (cc == 0) touched |= 1u << lo;
           }
-          if (umma::elect_one()) umma::mma_commit(b_empty + bs);
+          if (umma::elect_one()) umma::mma_commit(a_empty + as);   // frees the A stage once these MMAs have read it
           __syncwarp();
-          ++b_it;
+          ++a_it;
         }
+        if (umma::elect_one()) umma::mma_commit(b_empty + bs);
+        __syncwarp();
+        ++b_it;
       }
-      if (umma::elect_one()) umma::mma_commit(acc_full);
-      __syncwarp();
-      if (dbg && lane == 0) dbg[4] = clock64();
     }
+    if (umma::elect_one()) umma::mma_commit(acc_full);
+    __syncwarp();
+    if (dbg && lane == 0) dbg[4] = clock64();
   } else {
     // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th
     // 16-column unit of it (four warps share each 32-lane TMEM quarter) =====
     constexpr int kParts = kTcEpiWarps / 4;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which share of the column units (0..kParts-1)
+    const int part = (warp - 2) >> 2;             // which share of the column units (0..kParts-1)
     const int row_local = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int N = a.lout * a.ct;
@@ -278,10 +366,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     float mean[2] = {0.0f, 0.0f}, rstd[2] = {1.0f, 1.0f};
     if (a.mode != TC_BIAS) {
       // GroupNorm(8) over (cg channels x lout positions) of this row (blocks.py:24-26): two-pass,
-      // partial sums of the two column halves meet in shared memory
+      // partial sums of the column shares meet in shared memory
       const float inv_n = 1.0f / (float)(a.cg * a.lout);
       float s[2] = {0.0f, 0.0f};
-      for (int u = half; u < n_units; u += kParts) {
+      for (int u = part; u < n_units; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int c0 = (u * 16) % a.ct;
@@ -293,8 +381,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int i = 0; i < 8; ++i) { s[0] += v[i] + s_par[c0 + i]; s[1] += v[8 + i] + s_par[c0 + 8 + i]; }
         }
       }
-      s_stat[(half * 2 + 0) * 128 + row_local] = s[0];
-      s_stat[(half * 2 + 1) * 128 + row_local] = s[1];
+      s_stat[(part * 2 + 0) * 128 + row_local] = s[0];
+      s_stat[(part * 2 + 1) * 128 + row_local] = s[1];
       epi_barrier();
       {
         float t0 = 0.0f, t1 = 0.0f;
@@ -304,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         mean[1] = t1 * inv_n;
       }
       float ss[2] = {0.0f, 0.0f};
-      for (int u = half; u < n_units; u += kParts) {
+      for (int u = part; u < n_units; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int c0 = (u * 16) % a.ct;
@@ -322,8 +410,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
       }
       float* s2 = s_stat + kParts * 2 * 128;
-      s2[(half * 2 + 0) * 128 + row_local] = ss[0];
-      s2[(half * 2 + 1) * 128 + row_local] = ss[1];
+      s2[(part * 2 + 0) * 128 + row_local] = ss[0];
+      s2[(part * 2 + 1) * 128 + row_local] = ss[1];
       epi_barrier();
       {
         float t0 = 0.0f, t1 = 0.0f;
@@ -336,35 +424,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // Results are staged in shared memory (the operand stages are free once the accumulator is
     // complete) and written out cooperatively so every store instruction covers whole sectors:
     // a thread-per-row store pattern would touch 32 different 128-byte lines per instruction.
-    const int kch_out = a.cout >> 5;
-    float* stg = reinterpret_cast<float*>(a_smem);
+    // Staging per 16-column unit: [128 rows][UC x 16 B] hi, same for lo, [128 rows][64 B] residual.
+    const int kch_out = a.cout >> E::kShift;
     const int et = threadIdx.x - 64;               // index among the epilogue threads
     const int plain_stride = N + 1;                // odd row stride: conflict-free column writes
+    uint8_t* stg_hi = a_smem;
+    uint8_t* stg_lo = stg_hi + (size_t)a.epi_units * (128 * UC * 16);
+    float* stg_res = reinterpret_cast<float*>(stg_lo + (size_t)a.epi_units * (128 * UC * 16));
+    float* stg_plain = reinterpret_cast<float*>(a_smem);
+    const int sw_out = (UC == 4) ? ((row_local >> 1) & 3) : ((row_local >> 2) & 1);
     for (int u0 = 0; u0 < n_units; u0 += a.epi_units) {
       const int u1 = min(n_units, u0 + a.epi_units);
-      float* stg_lo = stg + (size_t)a.epi_units * 2048;
-      float* stg_res = stg + (size_t)a.epi_units * 4096;
       if (a.mode == TC_GN_RES_ID) {
         // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input, fetched
-        // with sector-coalesced loads into the staging area (same tile shape as the output)
-        const int items = (u1 - u0) * 512;
-        const int kch_res = a.res.C >> 5;
+        // with sector-coalesced loads into the staging area as fp32
+        const int items = (u1 - u0) * 128 * UC;
+        const int kch_res = a.res.C >> E::kShift;
         for (int idx = et; idx < items; idx += kTcEpiThreads) {
-          const int m = idx & 3, r = (idx >> 2) & 127, uu = idx >> 9;
+          const int m = idx % UC, r = (idx / UC) & 127, uu = idx / (UC * 128);
           const int u = u0 + uu;
           const int lo = (u * 16) / a.ct;
           const int k = lo * a.res.C + nt * a.ct + (u * 16) % a.ct;
-          const size_t src = ((size_t)rt * (a.lout * kch_res) + (k >> 5)) * kTcBlock + tc_swz(r, ((k & 31) >> 2) + m);
-          float4 h = *reinterpret_cast<const float4*>(a.res.hi + src);
-          if (a.res.lo) {
-            const float4 l = *reinterpret_cast<const float4*>(a.res.lo + src);
-            h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+          const int chunk = (((k & (E::kCpc - 1)) * (BF16 ? 2 : 4)) >> 4) + m;
+          const size_t src = ((size_t)rt * (a.lout * kch_res) + (k >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(r, chunk);
+          const uint4 h = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + src);
+          uint4 l = make_uint4(0, 0, 0, 0);
+          if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + src);
+          float x[8];
+          tc_chunk_sum<BF16>(h, l, a.res.lo != nullptr, x);
+          // residual staging row: 16 floats = 4 x 16 B, chunk q at position q ^ ((r>>1)&3)
+          float* dst = stg_res + (size_t)(uu * 128 + r) * 16;
+          const int rs = (r >> 1) & 3;
+          if (BF16) {
+            *reinterpret_cast<float4*>(dst + (((2 * m) ^ rs) << 2)) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(dst + (((2 * m + 1) ^ rs) << 2)) = make_float4(x[4], x[5], x[6], x[7]);
+          } else {
+            *reinterpret_cast<float4*>(dst + ((m ^ rs) << 2)) = make_float4(x[0], x[1], x[2], x[3]);
           }
-          *reinterpret_cast<float4*>(stg_res + (uu * 128 + r) * 16 + ((m ^ ((r >> 1) & 3)) << 2)) = h;
         }
         epi_barrier();
       }
-      for (int u = u0 + half; u < u1; u += kParts) {
+      for (int u = u0 + part; u < u1; u += kParts) {
         float v[16];
         umma::tmem_ld16(t_lane + a.ph[0].d_col + u * 16, v);
         const int lo = (u * 16) / a.ct;
@@ -386,10 +486,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
         } else if (a.mode == TC_GN_RES_ID) {
           const float* sr = stg_res + ((size_t)(u - u0) * 128 + row_local) * 16;
-          const int sw = (row_local >> 1) & 3;
+          const int rs = (row_local >> 1) & 3;
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
-            const float4 h = *reinterpret_cast<const float4*>(sr + ((m ^ sw) << 2));
+            const float4 h = *reinterpret_cast<const float4*>(sr + ((m ^ rs) << 2));
             v[m * 4 + 0] += h.x;
             v[m * 4 + 1] += h.y;
             v[m * 4 + 2] += h.z;
@@ -397,44 +497,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           }
         }
         if (a.out_hi) {
-          // staging tile of this unit: [128 rows][4 x 16 B], chunk m of row r at position m ^ ((r>>1)&3)
-          float* sh = stg + ((size_t)(u - u0) * 128 + row_local) * 16;
-          float* sl = stg_lo + ((size_t)(u - u0) * 128 + row_local) * 16;
-          const int sw = (row_local >> 1) & 3;
+          // staging tile of this unit: [128 rows][UC x 16 B], chunk m of row r at position m ^ sw_out
+          uint4 h[4], l[4];
+          tc_split_store<BF16>(v, a.out_lo != nullptr, h, l);
+          uint4* sh = reinterpret_cast<uint4*>(stg_hi + ((size_t)(u - u0) * 128 + row_local) * (UC * 16));
+          uint4* sl = reinterpret_cast<uint4*>(stg_lo + ((size_t)(u - u0) * 128 + row_local) * (UC * 16));
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            float4 h, l;
-            if (a.out_lo) {
-              h.x = umma::to_tf32(v[m * 4 + 0]); l.x = umma::to_tf32(v[m * 4 + 0] - h.x);
-              h.y = umma::to_tf32(v[m * 4 + 1]); l.y = umma::to_tf32(v[m * 4 + 1] - h.y);
-              h.z = umma::to_tf32(v[m * 4 + 2]); l.z = umma::to_tf32(v[m * 4 + 2] - h.z);
-              h.w = umma::to_tf32(v[m * 4 + 3]); l.w = umma::to_tf32(v[m * 4 + 3] - h.w);
-              *reinterpret_cast<float4*>(sl + ((m ^ sw) << 2)) = l;
-            } else {
-              h = make_float4(v[m * 4 + 0], v[m * 4 + 1], v[m * 4 + 2], v[m * 4 + 3]);
-            }
-            *reinterpret_cast<float4*>(sh + ((m ^ sw) << 2)) = h;
+          for (int m = 0; m < UC; ++m) {
+            sh[m ^ sw_out] = h[m];
+            if (a.out_lo) sl[m ^ sw_out] = l[m];
           }
         } else {
           // plain [row][c][l] staging: this CTA's channels are one contiguous run per row
-          float* sp = stg + (size_t)row_local * plain_stride + (size_t)c0 * a.lout + lo;
+          float* sp = stg_plain + (size_t)row_local * plain_stride + (size_t)c0 * a.lout + lo;
 #pragma unroll
           for (int i = 0; i < 16; ++i) sp[(size_t)i * a.lout] = v[i];
         }
       }
       epi_barrier();
       if (a.out_hi) {
-        const int items = (u1 - u0) * 512;          // (unit, row, 16-byte chunk)
+        const int items = (u1 - u0) * 128 * UC;          // (unit, row, 16-byte chunk)
         for (int idx = et; idx < items; idx += kTcEpiThreads) {
-          const int m = idx & 3, r = (idx >> 2) & 127, uu = idx >> 9;
+          const int m = idx % UC, r = (idx / UC) & 127, uu = idx / (UC * 128);
           if (rt * kTcRows + r >= a.rows) continue;
           const int u = u0 + uu;
           const int lo = (u * 16) / a.ct;
           const int k = lo * a.cout + nt * a.ct + (u * 16) % a.ct;
-          const size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> 5)) * kTcBlock + tc_swz(r, ((k & 31) >> 2) + m);
-          const int src = (uu * 128 + r) * 16 + ((m ^ ((r >> 1) & 3)) << 2);
-          *reinterpret_cast<float4*>(a.out_hi + dst) = *reinterpret_cast<const float4*>(stg + src);
-          if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst) = *reinterpret_cast<const float4*>(stg_lo + src);
+          const int chunk = (((k & (E::kCpc - 1)) * (BF16 ? 2 : 4)) >> 4) + m;
+          const size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(r, chunk);
+          const int sw = (UC == 4) ? ((r >> 1) & 3) : ((r >> 2) & 1);
+          const size_t src = ((size_t)(uu * 128 + r) * UC + (m ^ sw)) * 16;
+          *reinterpret_cast<uint4*>((uint8_t*)a.out_hi + dst) = *reinterpret_cast<const uint4*>(stg_hi + src);
+          if (a.out_lo) *reinterpret_cast<uint4*>((uint8_t*)a.out_lo + dst) = *reinterpret_cast<const uint4*>(stg_lo + src);
         }
       } else {
         // all units of a plain-output layer fit one round (host guarantees it)
@@ -443,7 +537,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const int grow = rt * kTcRows + r;
           if (grow >= a.rows) break;
           float* o = a.out_plain + ((size_t)grow * a.cout + (size_t)nt * a.ct) * a.lout;
-          const float* sp = stg + (size_t)r * plain_stride;
+          const float* sp = stg_plain + (size_t)r * plain_stride;
           for (int e = lane; e < N; e += 32) o[e] = sp[e];
         }
       }
@@ -460,40 +554,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
-// plain [rows][C][L] float32  ->  tiled hi/lo operand blocks (K order (l, c))
-__global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int L, float* __restrict__ hi,
-                               float* __restrict__ lo) {
-  // one thread per (row, l, 4 consecutive channels)
+// plain [rows][C][L] float32  ->  tiled hi/lo operand blocks (K order (l, c)); one thread per
+// (row, l, 16-byte chunk of channels)
+template <bool BF16>
+__global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int L, void* __restrict__ hi,
+                               void* __restrict__ lo) {
+  using E = TcElem<BF16>;
+  constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c4n = C >> 2;
-  const size_t total = (size_t)rows * L * c4n;
+  const int cn = C / EPC;
+  const size_t total = (size_t)rows * L * cn;
   if (i >= total) return;
-  const int c4 = (int)(i % c4n);
-  const int l = (int)((i / c4n) % L);
-  const int row = (int)(i / ((size_t)c4n * L));
+  const int cq = (int)(i % cn);
+  const int l = (int)((i / cn) % L);
+  const int row = (int)(i / ((size_t)cn * L));
   const int rt = row / kTcRows, rl = row % kTcRows;
-  float v[4];
+  float v[16];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = x[((size_t)row * C + c4 * 4 + e) * L + l];
-  const int k = l * C + c4 * 4;
-  const size_t blk = ((size_t)rt * (L * (C >> 5)) + (k >> 5)) * kTcBlock;
-  const int off = tc_swz(rl, (k & 31) >> 2);
-  float4 h, r;
-  if (lo) {
-    h.x = umma::to_tf32(v[0]); r.x = umma::to_tf32(v[0] - h.x);
-    h.y = umma::to_tf32(v[1]); r.y = umma::to_tf32(v[1] - h.y);
-    h.z = umma::to_tf32(v[2]); r.z = umma::to_tf32(v[2] - h.z);
-    h.w = umma::to_tf32(v[3]); r.w = umma::to_tf32(v[3] - h.w);
-    *reinterpret_cast<float4*>(lo + blk + off) = r;
-  } else {
-    h = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  *reinterpret_cast<float4*>(hi + blk + off) = h;
+  for (int e = 0; e < 16; ++e) v[e] = 0.0f;
+#pragma unroll
+  for (int e = 0; e < EPC; ++e) v[e] = x[((size_t)row * C + cq * EPC + e) * L + l];
+  const int k = l * C + cq * EPC;
+  const size_t blk = ((size_t)rt * (L * (C >> E::kShift)) + (k >> E::kShift)) * kTcBlockBytes;
+  const int off = tc_swz_bytes(rl, (k & (E::kCpc - 1)) / EPC);
+  uint4 h[4], r[4];
+  tc_split_store<BF16>(v, lo != nullptr, h, r);
+  *reinterpret_cast<uint4*>((uint8_t*)hi + blk + off) = h[0];
+  if (lo) *reinterpret_cast<uint4*>((uint8_t*)lo + blk + off) = r[0];
 }
 
-// tiled hi/lo -> plain [rows][C][L] (debug read-back and the tensor -> CUDA-core boundary)
-__global__ void tc_unpack_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int rows, int C, int L,
+// tiled hi/lo -> plain [rows][C][L] (debug read-back)
+template <bool BF16>
+__global__ void tc_unpack_kernel(const void* __restrict__ hi, const void* __restrict__ lo, int rows, int C, int L,
                                  float* __restrict__ x) {
+  using E = TcElem<BF16>;
+  constexpr int EPC = BF16 ? 8 : 4;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)rows * C * L;
   if (i >= total) return;
@@ -502,9 +597,19 @@ __global__ void tc_unpack_kernel(const float* __restrict__ hi, const float* __re
   const int row = (int)(i / ((size_t)C * L));
   const int rt = row / kTcRows, rl = row % kTcRows;
   const int k = l * C + c;
-  const size_t blk = ((size_t)rt * (L * (C >> 5)) + (k >> 5)) * kTcBlock;
-  const int off = tc_swz(rl, (k & 31) >> 2) + (k & 3);
-  x[i] = hi[blk + off] + (lo ? lo[blk + off] : 0.0f);
+  const size_t blk = ((size_t)rt * (L * (C >> E::kShift)) + (k >> E::kShift)) * kTcBlockBytes;
+  const int off = tc_swz_bytes(rl, (k & (E::kCpc - 1)) / EPC);
+  const int e = k % EPC;
+  if (BF16) {
+    const uint16_t h = *reinterpret_cast<const uint16_t*>((const uint8_t*)hi + blk + off + e * 2);
+    float v = __uint_as_float((uint32_t)h << 16);
+    if (lo) v += __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)lo + blk + off + e * 2) << 16);
+    x[i] = v;
+  } else {
+    float v = *reinterpret_cast<const float*>((const uint8_t*)hi + blk + off + e * 4);
+    if (lo) v += *reinterpret_cast<const float*>((const uint8_t*)lo + blk + off + e * 4);
+    x[i] = v;
+  }
 }
 
 }  // namespace edmp

@@ -183,7 +183,7 @@ size_t unet_param_count(const int* dims, int n_dims) {
 // ---- engine -----------------------------------------------------------------------------------------
 struct Act {
   float* p = nullptr;              // plain [rows][C][L] float32 (CUDA-core layers), may be null
-  float *thi = nullptr, *tlo = nullptr;  // tiled TF32 hi / lo operand blocks (tensor-core layers)
+  void *thi = nullptr, *tlo = nullptr;   // tiled hi / lo operand blocks (tensor-core layers)
   int C = 0, L = 0;
   bool ok = true;
 };
@@ -217,11 +217,13 @@ template <int OP> static double count_pairs(int lin, int lout) {
 struct UNet {
   int precision = 0;
   bool tc = false;        // tensor-core path for the L <= 7 levels
-  bool tc_split = false;  // 3xTF32 (hi/lo operands)
+  bool tc_split = false;  // three-MMA hi/lo operand split
+  bool tc_bf16 = false;   // BF16 operand elements (else TF32)
+  int cpc() const { return tc_bf16 ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   int max_rows = 0;
   int n_launches = 0;
-  std::vector<float*> dev_allocs;
+  std::vector<void*> dev_allocs;
   std::vector<Layer> layers;
   std::map<std::string, Act> acts;
   float* temb = nullptr;  // [255][temb_width]
@@ -232,15 +234,18 @@ struct UNet {
   int final_c = 0;
 };
 
-static float* upload(UNet* u, const std::vector<float>& v) {
-  float* p = nullptr;
-  if (cudaMalloc(&p, v.size() * sizeof(float)) != cudaSuccess) return nullptr;
-  if (cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+static void* upload_bytes(UNet* u, const void* data, size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(p, data, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(p);
     return nullptr;
   }
   u->dev_allocs.push_back(p);
   return p;
+}
+static float* upload(UNet* u, const std::vector<float>& v) {
+  return static_cast<float*>(upload_bytes(u, v.data(), v.size() * sizeof(float)));
 }
 
 static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = true, bool tiled = false) {
@@ -253,12 +258,12 @@ static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = 
   }
   if (ok && tiled) {
     // row tiles of 128; zero-filled once so the padding rows of the last tile stay finite
-    const size_t n = (size_t)((u->max_rows + kTcRows - 1) / kTcRows) * L * (C / kTcChunk) * kTcBlock;
-    ok = cudaMalloc(&a.thi, n * sizeof(float)) == cudaSuccess;
-    if (ok) { u->dev_allocs.push_back(a.thi); cudaMemset(a.thi, 0, n * sizeof(float)); }
+    const size_t n = (size_t)((u->max_rows + kTcRows - 1) / kTcRows) * L * (C / u->cpc()) * kTcBlockBytes;
+    ok = cudaMalloc(&a.thi, n) == cudaSuccess;
+    if (ok) { u->dev_allocs.push_back(a.thi); cudaMemset(a.thi, 0, n); }
     if (ok && u->tc_split) {
-      ok = cudaMalloc(&a.tlo, n * sizeof(float)) == cudaSuccess;
-      if (ok) { u->dev_allocs.push_back(a.tlo); cudaMemset(a.tlo, 0, n * sizeof(float)); }
+      ok = cudaMalloc(&a.tlo, n) == cudaSuccess;
+      if (ok) { u->dev_allocs.push_back(a.tlo); cudaMemset(a.tlo, 0, n); }
     }
   }
   if (!ok) { a.p = nullptr; a.thi = nullptr; a.ok = false; return a; }
@@ -376,34 +381,60 @@ struct Builder {
     return r;
   }
 
-  // Packs weights into UMMA-ready tiles [n_tile][c_chunk][slots*ct rows][32 floats], SWIZZLE_128B,
-  // K-major; wfn(co, ci, slot) supplies the value.  Produces the TF32 hi part and (3xTF32) the lo
-  // remainder.
+  static uint16_t bf16_round(float x) {  // round to nearest even
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    b += 0x7FFFu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+  }
+  static float bf16_to_float(uint16_t h) {
+    uint32_t b = (uint32_t)h << 16;
+    float r;
+    std::memcpy(&r, &b, 4);
+    return r;
+  }
+
+  // Packs weights into UMMA-ready tiles [n_tile][c_chunk][slots*ct rows][128 B], SWIZZLE_128B,
+  // K-major; wfn(co, ci, slot) supplies the value.  Produces the hi part and (split modes) the lo
+  // remainder in the operand element type (TF32-rounded fp32 or BF16).
   template <class F>
-  void pack_tc(int cout, int cin, int ct, int slots, F wfn, const float** hi_out, const float** lo_out) {
-    const int n_tiles = cout / ct, kch = cin / kTcChunk;
-    const size_t tile = (size_t)slots * ct * kTcChunk;
-    std::vector<float> hi(tile * n_tiles * kch), lo(u->tc_split ? hi.size() : 0);
+  void pack_tc(int cout, int cin, int ct, int slots, F wfn, const void** hi_out, const void** lo_out) {
+    const int cpc = u->cpc(), ebytes = u->tc_bf16 ? 2 : 4, epc = 16 / ebytes;
+    const int n_tiles = cout / ct, kch = cin / cpc;
+    const size_t tile = (size_t)slots * ct * 128;   // bytes
+    std::vector<uint8_t> hi(tile * n_tiles * kch), lo(u->tc_split ? hi.size() : 0);
     for (int nt = 0; nt < n_tiles; ++nt)
       for (int cc = 0; cc < kch; ++cc) {
         const size_t base = ((size_t)nt * kch + cc) * tile;
         for (int sl = 0; sl < slots; ++sl)
           for (int c = 0; c < ct; ++c) {
             const int r = sl * ct + c;
-            for (int e = 0; e < kTcChunk; ++e) {
-              const float w = wfn(nt * ct + c, cc * kTcChunk + e, sl);
-              const size_t off = base + (size_t)r * 32 + ((((e >> 2) ^ (r & 7)) << 2) | (e & 3));
-              const float h = tf32_round(w);
-              hi[off] = h;
-              if (u->tc_split) lo[off] = tf32_round(w - h);
+            for (int e = 0; e < cpc; ++e) {
+              const float w = wfn(nt * ct + c, cc * cpc + e, sl);
+              const size_t off = base + (size_t)r * 128 + ((((e / epc) ^ (r & 7)) << 4) | ((e % epc) * ebytes));
+              if (u->tc_bf16) {
+                const uint16_t h = bf16_round(w);
+                std::memcpy(&hi[off], &h, 2);
+                if (u->tc_split) {
+                  const uint16_t l = bf16_round(w - bf16_to_float(h));
+                  std::memcpy(&lo[off], &l, 2);
+                }
+              } else {
+                const float h = tf32_round(w);
+                std::memcpy(&hi[off], &h, 4);
+                if (u->tc_split) {
+                  const float l = tf32_round(w - h);
+                  std::memcpy(&lo[off], &l, 4);
+                }
+              }
             }
           }
       }
-    *hi_out = upload(u, hi);
+    *hi_out = upload_bytes(u, hi.data(), hi.size());
     ok = ok && *hi_out;
     *lo_out = nullptr;
     if (u->tc_split) {
-      *lo_out = upload(u, lo);
+      *lo_out = upload_bytes(u, lo.data(), lo.size());
       ok = ok && *lo_out;
     }
   }
@@ -414,7 +445,7 @@ struct Builder {
     const int nparts = t.split ? 2 : 1;
     int max_slots = t.ph[0].slots;
     if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
-    const size_t a_stage = (size_t)kTcBlock * 4 * nparts;
+    const size_t a_stage = (size_t)kTcBlockBytes * nparts;
     const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
     const size_t budget = 232448 - 1024 - 1024 - 10240;   // dynamic limit - alignment slack - barriers - static smem
     t.b_stages = (2 * b_stage + 2 * a_stage <= budget) ? 2 : 1;
@@ -432,8 +463,9 @@ struct Builder {
       ok = ok && need <= budget;
       t.epi_units = (n_units + 3) & ~3;
     } else {
-      // per 16-column unit: 8 KB hi + 8 KB lo output staging (+ 8 KB residual staging)
-      const size_t per_unit = t.mode == TC_GN_RES_ID ? 24576 : 16384;
+      // per 16-column unit: hi + lo output staging (128 rows x 64 B tf32 / 32 B bf16 each) + 8 KB residual
+      const size_t out_unit = (size_t)128 * (u->tc_bf16 ? 32 : 64) * 2;
+      const size_t per_unit = out_unit + (t.mode == TC_GN_RES_ID ? 8192 : 0);
       stage_total = std::max(stage_total, 4 * per_unit);
       const int cap = (int)(stage_total / per_unit);
       t.epi_units = std::max(4, std::min((n_units + 3) & ~3, cap & ~3));
@@ -626,9 +658,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   EDMP_REQUIRE(n_dims == 6 && dims[0] == 32 && dims[1] == 64 && dims[2] == 128 && dims[3] == 256 &&
                    dims[4] == 512 && dims[5] == 512,
                "only dims=(32,64,128,256,512,512) is compiled in (infer_serial.py:50)");
-  EDMP_REQUIRE(precision == EDMP_PRECISION_FP32 || precision == EDMP_PRECISION_TF32X3 ||
-                   precision == EDMP_PRECISION_TF32,
-               "precision must be fp32, tf32x3 or tf32 (bf16 modes are not built yet)");
+  EDMP_REQUIRE(precision >= EDMP_PRECISION_FP32 && precision <= EDMP_PRECISION_BF16,
+               "precision must be one of fp32, tf32x3, tf32, bf16x3, bf16");
   EDMP_REQUIRE(max_rows > 0, "max_rows must be positive");
   ParamWalker pw;
   walk_params(dims, n_dims, pw);
@@ -638,11 +669,13 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->precision = precision;
   u->max_rows = max_rows;
   u->tc = precision != EDMP_PRECISION_FP32;
-  u->tc_split = precision == EDMP_PRECISION_TF32X3;
+  u->tc_split = precision == EDMP_PRECISION_TF32X3 || precision == EDMP_PRECISION_BF16X3;
+  u->tc_bf16 = precision == EDMP_PRECISION_BF16X3 || precision == EDMP_PRECISION_BF16;
   if (u->tc) {
     static bool attr_set = false;
     if (!attr_set) {
-      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       attr_set = true;
     }
   }
@@ -736,7 +769,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
 
 void unet_destroy(UNet* u) {
   if (!u) return;
-  for (float* p : u->dev_allocs) cudaFree(p);
+  for (void* p : u->dev_allocs) cudaFree(p);
   delete u;
 }
 
@@ -758,11 +791,15 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
     dim3 grid((rows + kTcRows - 1) / kTcRows, ly.tc_tiles);
-    conv_tc_kernel<<<grid, kTcThreads, ly.tc_smem, st>>>(a);
+    if (u->tc_bf16) conv_tc_kernel<true><<<grid, kTcThreads, ly.tc_smem, st>>>(a);
+    else conv_tc_kernel<false><<<grid, kTcThreads, ly.tc_smem, st>>>(a);
   } else {
-    const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / 4);
-    tc_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C,
-                                                                  ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
+    const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / (u->tc_bf16 ? 8 : 4));
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (u->tc_bf16)
+      tc_pack_kernel<true><<<blocks, 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C, ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
+    else
+      tc_pack_kernel<false><<<blocks, 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C, ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
   }
 }
 
@@ -852,7 +889,8 @@ int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C
     if (a.p) {
       EDMP_CK(cudaMemcpyAsync(out, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-      tc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
+      if (u->tc_bf16) tc_unpack_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
+      else tc_unpack_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
       EDMP_CK(cudaGetLastError());
     }
   }
