@@ -1,6 +1,7 @@
 // extern "C" boundary of libedmp_b200.so -- see include/edmp_b200.h for the contract.
 #include "edmp_b200.h"
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -11,6 +12,10 @@
 namespace edmp {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
+bool pdl_enabled() {
+  static const bool on = std::getenv("EDMP_NO_PDL") == nullptr;
+  return on;
+}
 }  // namespace edmp
 
 using namespace edmp;

@@ -33,6 +33,30 @@ constexpr int kRowElems = kHorizon * kDof;  // 350
 constexpr int kTSteps = 255;
 constexpr int kMaxObs = 64;
 
+// Programmatic dependent launch: every kernel of the per-step chain lets its successor start
+// launching at once (the successor's prologue -- barrier init, TMEM allocation, parameter staging,
+// launch latency -- overlaps this kernel's execution on the idle SMs) and waits for its predecessor
+// to complete before touching activations.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // x * tanh(softplus(x)) (reference blocks.py:27 nn.Mish), via tanh(log1p(e^x)) = n/(n+2), n = e^x(e^x+2).
 __device__ __forceinline__ float mish_f(float x) {
   if (x > 20.0f) return x;

@@ -52,7 +52,7 @@ struct ConvArgs {
   int rows, cout;
 };
 
-constexpr int kKC = 8;  // input channels per shared-memory K chunk
+constexpr int kKC = 16;  // input channels per shared-memory K chunk
 
 template <int OP, int LIN, int LOUT, int TR, int TC, int RB, int NCB>
 struct ConvTile {
@@ -135,6 +135,8 @@ conv_fused_kernel(ConvArgs a) {
   float* Ws = smem + Tile::XS_FLOATS;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int row0 = blockIdx.x * RB, co0 = blockIdx.y * NCB;
+  pdl_launch_dependents();
+  pdl_wait();
 
   float acc[TR][TC][LOUT];
 #pragma unroll

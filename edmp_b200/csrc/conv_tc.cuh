@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int rt = blockIdx.x, nt = blockIdx.y;
   long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     // one arrival per producer thread on the "full" barriers (hi and lo parts have their own thread)
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel; activations are read below
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   // ===== producers: bulk async copies of ready-made operand tiles.  One thread can keep only ~2
@@ -561,6 +563,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int
                                void* __restrict__ lo) {
   using E = TcElem<BF16>;
   constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int cn = C / EPC;
   const size_t total = (size_t)rows * L * cn;

@@ -269,6 +269,8 @@ __global__ void __launch_bounds__(64) guide_grad_kernel(const SceneDev* __restri
   __shared__ double s_red[2];
   const int row = blockIdx.x;
   const int w = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   stage_obstacles(sc, t != 0, t != 0 ? expansion[(size_t)row * kTSteps + t - 1] : 0.0,
                   t != 0 ? clearance[(size_t)row * kTSteps + t - 1] : 0.0, s_omin, s_omax);
   if (threadIdx.x < 27) s_half[threadIdx.x] = sc->link_half[threadIdx.x / 3][threadIdx.x % 3];
@@ -356,6 +358,8 @@ __global__ void __launch_bounds__(128) guide_apply_kernel(const float* __restric
                                                           double* __restrict__ x, float* __restrict__ xf) {
   __shared__ double s_red[4];
   __shared__ float s_norm;
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int e0 = (row / ensemble_rows) * ensemble_rows;
   double s = 0.0;
@@ -593,10 +597,11 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
   EDMP_REQUIRE(n_inner >= 1 && n_inner <= 64, "n_inner must be in 1..64");
   if (ensure_work(s, rows, n_inner)) return 1;
   EndPoints ep = make_endpoints(start_h, goal_h);
-  guide_grad_kernel<<<rows, 64, 0, st>>>(s->dev, x, ld, off, n_inner, clip, ep, t, s->clearance,
-                                         s->expansion, s->method, s->raw, s->rowsq);
-  guide_apply_kernel<<<rows, 128, 0, st>>>(s->raw, s->rowsq, n_inner, s->ensemble_rows, s->grad_norm,
-                                           s->schedule, t, grad_out, x_state, xf_state);
+  launch_pdl(guide_grad_kernel, dim3(rows), dim3(64), 0, st, (const SceneDev*)s->dev, x, ld, off, n_inner, clip, ep, t,
+             (const double*)s->clearance, (const double*)s->expansion, (const unsigned char*)s->method, s->raw, s->rowsq);
+  launch_pdl(guide_apply_kernel, dim3(rows), dim3(128), 0, st, (const float*)s->raw, (const double*)s->rowsq, n_inner,
+             s->ensemble_rows, (const unsigned char*)s->grad_norm, (const double*)s->schedule, t, grad_out, x_state,
+             xf_state);
   EDMP_CK(cudaGetLastError());
   if (raw_out)
     EDMP_CK(cudaMemcpyAsync(raw_out, s->raw, (size_t)rows * 7 * n_inner * sizeof(float),

@@ -76,6 +76,8 @@ __global__ void condition_kernel(double* __restrict__ x, float* __restrict__ xf,
 __global__ void posterior_kernel(double* __restrict__ x, float* __restrict__ xf,
                                  const float* __restrict__ eps, const double* __restrict__ noise,
                                  uint64_t seed, int t, int ensemble_rows, StepCoef sc, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int row = (int)(i / kRowElems);
@@ -157,7 +159,7 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
     sc.sqrt_alpha = std::sqrt(a);
     sc.beta = s->beta[t - 1];
     const double* z = noise ? noise + (size_t)(t_start - t) * n : nullptr;
-    posterior_kernel<<<blocks, threads, 0, st>>>(x, s->xf, s->eps, z, seed, t, ens, sc, n);
+    launch_pdl(posterior_kernel, dim3(blocks), dim3(threads), 0, st, x, s->xf, (const float*)s->eps, z, seed, t, ens, sc, n);
     ++launches;
     // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)
     if (scene && (t % 2) == 0 && t >= 5) {

@@ -27,11 +27,11 @@ namespace edmp {
 template <int LOUT, int COUT> struct TileCfg;
 #define EDMP_TILE(L, C, TR_, TC_, RB_, NCB_) \
   template <> struct TileCfg<L, C> { static constexpr int TR = TR_, TC = TC_, RB = RB_, NCB = NCB_; }
-EDMP_TILE(50, 32, 1, 2, 4, 32);
-EDMP_TILE(25, 32, 1, 2, 4, 32);
-EDMP_TILE(25, 64, 1, 4, 4, 64);
-EDMP_TILE(13, 64, 2, 4, 8, 64);
-EDMP_TILE(13, 128, 2, 4, 8, 64);
+EDMP_TILE(50, 32, 1, 1, 4, 32);
+EDMP_TILE(25, 32, 1, 1, 8, 32);
+EDMP_TILE(25, 64, 1, 2, 4, 64);
+EDMP_TILE(13, 64, 1, 2, 4, 64);
+EDMP_TILE(13, 128, 1, 2, 4, 64);
 EDMP_TILE(7, 128, 4, 4, 16, 64);
 EDMP_TILE(7, 256, 4, 4, 16, 64);
 EDMP_TILE(4, 256, 4, 4, 32, 64);
@@ -46,8 +46,8 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   using C = TileCfg<LOUT, COUT>;
   using Tile = ConvTile<OP, LIN, LOUT, C::TR, C::TC, C::RB, C::NCB>;
   dim3 grid((a.rows + C::RB - 1) / C::RB, COUT / C::NCB);
-  conv_fused_kernel<OP, LIN, LOUT, C::TR, C::TC, C::RB, C::NCB, GN, RES>
-      <<<grid, Tile::THREADS, Tile::SMEM_FLOATS * sizeof(float), st>>>(a);
+  launch_pdl(conv_fused_kernel<OP, LIN, LOUT, C::TR, C::TC, C::RB, C::NCB, GN, RES>, grid, dim3(Tile::THREADS),
+             Tile::SMEM_FLOATS * sizeof(float), st, a);
   return 0;
 }
 
@@ -88,8 +88,10 @@ static ConvLaunchFn pick_up(int lin, int c) {
 __global__ void final_pw_kernel(const float* __restrict__ h, const float* __restrict__ w /*[7][C]*/,
                                 const float* __restrict__ b, int C, int rows, float* __restrict__ eps) {
   extern __shared__ float sw[];
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 7 * C + 7; i += blockDim.x) sw[i] = i < 7 * C ? w[i] : b[i - 7 * C];
   __syncthreads();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * kHorizon) return;
   const int row = (int)(i / kHorizon), l = (int)(i % kHorizon);
@@ -791,15 +793,17 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
     dim3 grid((rows + kTcRows - 1) / kTcRows, ly.tc_tiles);
-    if (u->tc_bf16) conv_tc_kernel<true><<<grid, kTcThreads, ly.tc_smem, st>>>(a);
-    else conv_tc_kernel<false><<<grid, kTcThreads, ly.tc_smem, st>>>(a);
+    if (u->tc_bf16) launch_pdl(conv_tc_kernel<true>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
+    else launch_pdl(conv_tc_kernel<false>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
   } else {
     const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / (u->tc_bf16 ? 8 : 4));
     const unsigned blocks = (unsigned)((total + 255) / 256);
     if (u->tc_bf16)
-      tc_pack_kernel<true><<<blocks, 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C, ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
+      launch_pdl(tc_pack_kernel<true>, dim3(blocks), dim3(256), 0, st, (const float*)ly.pack_src.p, rows, ly.pack_src.C,
+                 ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
     else
-      tc_pack_kernel<false><<<blocks, 256, 0, st>>>(ly.pack_src.p, rows, ly.pack_src.C, ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
+      launch_pdl(tc_pack_kernel<false>, dim3(blocks), dim3(256), 0, st, (const float*)ly.pack_src.p, rows, ly.pack_src.C,
+                 ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
   }
 }
 
@@ -810,8 +814,9 @@ int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStrea
   for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, st);
   const int threads = 128;
   const size_t n = (size_t)rows * kHorizon;
-  final_pw_kernel<<<(unsigned)((n + threads - 1) / threads), threads, (7 * u->final_c + 7) * sizeof(float), st>>>(
-      u->final_in.p, u->final_w, u->final_b, u->final_c, rows, eps);
+  launch_pdl(final_pw_kernel, dim3((unsigned)((n + threads - 1) / threads)), dim3(threads),
+             (7 * u->final_c + 7) * sizeof(float), st, (const float*)u->final_in.p, (const float*)u->final_w,
+             (const float*)u->final_b, u->final_c, rows, eps);
   EDMP_CK(cudaGetLastError());
   return 0;
 }
