@@ -149,18 +149,20 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, note="CPU arm runs a bounded sample of the same workload"),
+            "config": workload_config(args.gpus, note="CPU arm runs a bounded sample of the same workload",
+                                      rows_per_guide=args.rows_per_guide),
             "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, note=None, precision="fp32"):
-    rows = len(GUIDES) * ROWS_PER_GUIDE
+def workload_config(n_gpus, note=None, precision="fp32", rows_per_guide=None):
+    rpg = rows_per_guide or ROWS_PER_GUIDE
+    rows = len(GUIDES) * rpg
     cfg = {"workload": "configs[1]: guided ensemble, guides %s x %d rows = %d rows/GPU (%d total), %d obstacles, "
-                       "T=255, horizon 50, 7 DoF" % (GUIDES, ROWS_PER_GUIDE, rows, rows * n_gpus, N_OBSTACLES),
-           "rows_per_gpu": rows, "n_guides": len(GUIDES), "rows_per_guide": ROWS_PER_GUIDE,
+                       "T=255, horizon 50, 7 DoF" % (GUIDES, rpg, rows, rows * n_gpus, N_OBSTACLES),
+           "rows_per_gpu": rows, "n_guides": len(GUIDES), "rows_per_guide": rpg,
            "obstacles": N_OBSTACLES, "precision_mode": precision, "parallelism": "dp%d (ensembles rank-local)" % n_gpus,
            "l2": "working set per pass (114 MB weights + ~250 KB activations/row) exceeds the 126 MB L2; "
                  "no explicit flush"}
@@ -192,7 +194,7 @@ def run_gpu_arm(args):
     model = TemporalUNet(os.path.join(tempfile.mkdtemp(), "TemporalUNetModel255_N50"), 7, 32, dev,
                          dims=(32, 64, 128, 256, 512, 512), precision=args.precision)
     model.load_state_dict(sd)
-    cfgs, scene, x_T, start, goal = build_workload(seed_offset=rank)
+    cfgs, scene, x_T, start, goal = build_workload(seed_offset=rank, rows_per_guide=args.rows_per_guide)
     rows = cfgs["total_batch_size"]
     guide = IntersectionVolumeGuide(scene, dev, cfgs, rows)
     diff = Diffusion(255, dev)
@@ -318,7 +320,7 @@ def run_gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
-                "config": workload_config(world, precision=args.precision),
+                "config": workload_config(world, precision=args.precision, rows_per_guide=args.rows_per_guide),
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": rows * 350 * 8,
                         "d2h_bytes_per_step": rows * 350 * 8 + rows * 4},
@@ -338,6 +340,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "tf32x3"),
                     help="fp32 (CUDA cores) | tf32x3 (tcgen05, 3xTF32, parity grade) | tf32 (tcgen05 single pass)")
+    ap.add_argument("--rows-per-guide", type=int, default=ROWS_PER_GUIDE,
+                    help="trajectory rows per guide per GPU (x %d guides = rows per GPU)" % len(GUIDES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-out", default=None, help="write the per-kernel time table of one UNet forward here")
     args = ap.parse_args()

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libedmp_b200.so")
 
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16x3": 3, "bf16": 4}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16x3": 3, "bf16": 4, "f16x3": 5, "f16": 6}
 
 c_void_p, c_int, c_size_t, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_char_p
 c_double, c_uint64, c_longlong = ctypes.c_double, ctypes.c_uint64, ctypes.c_longlong

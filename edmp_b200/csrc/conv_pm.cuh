@@ -1,0 +1,413 @@
+// Position-major tensor-core (tcgen05 + TMEM) convolution kernel for the long-horizon levels of the
+// TemporalUNet (horizon 25 and 50: few channels, many positions).
+//
+// conv_tc.cuh puts trajectory rows on the MMA's M axis and every output position on the N axis; that
+// stops at 512 TMEM columns (horizon 13).  Here the M axis is (position, row) instead:
+//
+//   * a CTA owns a block of 8 trajectory rows and ALL positions of a layer;
+//   * MMA lane m of M tile mt  <->  output index 16*mt + m/8, trajectory row m%8;
+//   * activations live in HBM as ready-made UMMA shared-memory images in "position-major" order:
+//       [row block][padded position p = l + 2, 0 .. L+3][8 rows][C halves]   (hi part and lo part)
+//     one swizzle atom (8 rows x 2C bytes, C = 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B) per position,
+//     positions -2,-1,L,L+1 are zero (the convolution's zero padding).  Neighbouring positions are
+//     exactly one atom apart, so
+//       - a filter tap is a START-ADDRESS offset of the A descriptor (no im2col, no data movement),
+//       - the stride-2 of nn.Conv1d(k=3,s=2,p=1) is a doubled STRIDE-BYTE-OFFSET,
+//       - nn.ConvTranspose1d(k=4,s=2,p=1) is two interleaved 2-tap convolutions (even / odd outputs);
+//   * N = C_out (32 or 64), K = C_in per tap; the whole layer's operands (activation image + all
+//     taps' weights) fit in shared memory, fetched with a handful of 1-D bulk async copies;
+//   * accumulators: one TMEM column block per (accumulator group, M tile); an optional auxiliary
+//     group computes the block's 1x1 residual conv (blocks.py:151) from the same activation image;
+//   * epilogue (8 warps): tcgen05.ld -> GroupNorm(8) over (C/8 channels x L positions) of each row
+//     (two-pass; the lanes sharing a row meet through warp shuffles, warps/tiles through shared
+//     memory) -> Mish -> + time embedding -> + identity residual -> hi/lo split -> stores in the
+//     layout the consumer wants (position-major, the rows-as-M tiles of conv_tc.cuh for the
+//     25 -> 13 down-sampling, or -- final block -- the fused nn.Conv1d(32, 7, 1) straight to eps).
+//
+// Reference ops covered: Conv1dBlock (blocks.py:13-34), ResidualConvolutionBlock (:137-166),
+// DownSampler's Conv1d(k3,s2,p1) (:211), UpSampler's ConvTranspose1d(k4,s2,p1) (:249), final_conv
+// (temporalunet.py:35-36).  16-bit operand elements only (IEEE half or BF16, hi/lo split or single).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace edmp {
+
+constexpr int kPmRows = 8;                  // trajectory rows per CTA (one swizzle atom of rows)
+constexpr int kPmEpiWarps = 8;
+constexpr int kPmEpiThreads = kPmEpiWarps * 32;
+constexpr int kPmThreads = 64 + kPmEpiThreads;   // warp 0: producer, warp 1: TMEM + MMA, 8 epilogue warps
+constexpr int kPmMaxTerms = 6;
+
+struct PmAct {          // position-major activation: [row block][L + 4][8][C] halves, hi and lo images
+  const void* hi;
+  const void* lo;
+  int C;
+};
+
+struct PmTerm {         // one (tap) contribution: D[acc group] += A(shifted by `off` atoms) * W[slot]
+  int8_t acc, slot, off, pad;
+};
+
+enum PmMode { PM_BIAS = 0, PM_GN = 1, PM_GN_RES = 2 };
+
+struct PmArgs {
+  PmAct a, b;           // inputs (b.C == 0 unless skip concat); same C, same horizon
+  int lin;              // input horizon
+  int n_m;              // output indices per accumulator group (lout, or lin for the transposed conv)
+  int lout;             // horizon of the output tensor(s)
+  int stride;           // A-side position stride (2 for the stride-2 conv)
+  int n_terms;
+  PmTerm terms[kPmMaxTerms];
+  int n_groups;         // accumulator groups: 1, or 2 for the transposed conv; the aux group comes on top
+  int aux;              // 1: extra group = 1x1 residual conv of the input, written to aux_hi/lo (bias only)
+  int out_step, out_off[2];   // output position of index i in group g: out_step * i + out_off[g]
+  int cout;
+  int mode;
+  int split;
+  int a_bytes_img;      // bytes of one activation image (lin + 4 atoms)
+  int a_bytes_total;    // shared-memory bytes reserved for the activation images incl. over-read tail
+  int w_bytes_part;     // bytes of all weight slots (one part)
+  int tmem_cols;        // power of two >= 32
+  float acc_scale, aux_scale;
+  const void *w_hi, *w_lo;          // [slot][k chunk][cout rows][2C bytes] swizzled
+  const float *bias, *gamma, *beta, *temb, *aux_bias;
+  PmAct res;            // identity residual source (PM_GN_RES), C == cout, horizon == lout
+  void *out_hi, *out_lo;            // position-major output (C = cout, horizon lout), may be null
+  void *aux_hi, *aux_lo;
+  void *tc_hi, *tc_lo;              // rows-as-M tiled output (conv_tc.cuh layout), may be null
+  const float *fw, *fb;             // fused final 1x1 conv [7][cout], [7]
+  float* eps;                       // [rows][7][lout]
+  int rows;
+};
+
+// swizzle of 16-byte chunk `c` in row `r` of an atom with `rby`-byte rows (rby = 32 / 64 / 128)
+__device__ __forceinline__ int pm_swz(int rby, int r, int c) {
+  return rby == 128 ? (c ^ (r & 7)) : (rby == 64 ? (c ^ ((r >> 1) & 3)) : (c ^ ((r >> 2) & 1)));
+}
+
+__device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, int rby) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(rby == 128 ? 2 : (rby == 64 ? 4 : 6)) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void pm_epi_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kPmEpiThreads) : "memory"); }
+
+template <int EL, int COUT>
+__global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_constant__ PmArgs a) {
+  static_assert(EL != TC_EL_TF32, "position-major kernels use 16-bit operand elements");
+  constexpr int UNITS = COUT / 16;            // 16-column accumulator units per M tile
+  constexpr int CG = COUT / 8;                // channels per GroupNorm group (4 or 8)
+  constexpr int GPU_ = 16 / CG;               // groups per unit (4 or 2)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full, bar_acc;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_par[5 * 64];             // bias | gamma | beta | temb | aux bias
+  __shared__ float s_fw[7 * 64 + 8];          // final 1x1 conv weights + bias
+  __shared__ float s_red[2][kPmEpiWarps][8][8];   // [pass][warp][row][group]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x;
+  const int C = a.a.C;
+  const int rby = 2 * C;                      // bytes per (position, row) line
+  const int atom = 8 * rby;
+  const int nkc = a.b.C ? 2 : 1;
+  const int nparts = a.split ? 2 : 1;
+  const int ntiles = (a.n_m + 15) >> 4;
+  uint8_t* a_smem = smem;                                   // [part][source] images
+  uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][cout][rby]
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&bar_full, 1);
+    umma::mbar_init(&bar_acc, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    // runtime column count (32 .. 512, power of two)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(&tmem_slot)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;
+    if (e < COUT) {
+      s_par[e] = a.bias ? a.bias[e] : 0.0f;
+      s_par[64 + e] = a.gamma ? a.gamma[e] : 1.0f;
+      s_par[128 + e] = a.beta ? a.beta[e] : 0.0f;
+      s_par[192 + e] = a.temb ? a.temb[e] : 0.0f;
+      s_par[256 + e] = a.aux_bias ? a.aux_bias[e] : 0.0f;
+    }
+    if (a.eps) {
+      for (int i = e; i < 7 * COUT + 7; i += kPmEpiThreads) s_fw[i] = i < 7 * COUT ? a.fw[i] : a.fb[i - 7 * COUT];
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== producer: the layer's whole operand set in a few bulk copies =====
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)(nparts * (nkc * a.a_bytes_img + a.w_bytes_part));
+      umma::mbar_arrive_expect_tx(&bar_full, total);
+      for (int p = 0; p < nparts; ++p) {
+        for (int s = 0; s < nkc; ++s) {
+          const PmAct& src = s ? a.b : a.a;
+          const uint8_t* g = (const uint8_t*)(p ? src.lo : src.hi) + (size_t)rb * a.a_bytes_img;
+          umma::bulk_g2s(a_smem + (size_t)(p * nkc + s) * a.a_bytes_img, g, (uint32_t)a.a_bytes_img, &bar_full);
+        }
+        umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, p ? a.w_lo : a.w_hi, (uint32_t)a.w_bytes_part, &bar_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
+    umma::mbar_wait(&bar_full, 0);
+    umma::tc_fence_after();
+    const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
+    const uint32_t a_lo_off = (uint32_t)(nkc * a.a_bytes_img), w_lo_off = (uint32_t)a.w_bytes_part;
+    const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
+    const int ksteps = C >> 4;
+    const int n_acc = a.n_groups + a.aux;
+    for (int mt = 0; mt < ntiles; ++mt) {
+      uint32_t touched = 0;
+      for (int ti = 0; ti < a.n_terms; ++ti) {
+        const PmTerm t = a.terms[ti];
+        const uint32_t d = tmem_base + (uint32_t)((t.acc * ntiles + mt) * COUT);
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
+          const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
+          const uint64_t da_hi = pm_desc(a_addr, a.stride * atom, rby), da_lo = pm_desc(a_addr + a_lo_off, a.stride * atom, rby);
+          const uint64_t db_hi = pm_desc(w_addr, atom, rby), db_lo = pm_desc(w_addr + w_lo_off, atom, rby);
+          const uint32_t acc0 = (touched >> t.acc) & 1u;
+          if (umma::elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t acc = acc0 | (uint32_t)(ks > 0);
+              if (a.split) {
+                umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+              } else {
+                umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+              }
+            }
+          }
+          __syncwarp();
+          touched |= 1u << t.acc;
+        }
+      }
+    }
+    (void)n_acc;
+    if (umma::elect_one()) umma::mma_commit(&bar_acc);
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access (warp id mod 4)
+    const int half = ew >> 2;                   // which M tiles (mt & 1 == half)
+    const int row = lane & 7;
+    const int pos_in_tile = quarter * 4 + (lane >> 3);
+    const int grow = rb * kPmRows + row;        // global trajectory row
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    umma::mbar_wait(&bar_acc, 0);
+    __syncwarp();
+    umma::tc_fence_after();
+
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { mean[g] = 0.0f; rstd[g] = 1.0f; }
+    if (a.mode != PM_BIAS) {
+      // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26), two-pass
+      const float inv_n = 1.0f / (float)(CG * a.n_m);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float s[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s[g] = 0.0f;
+        for (int mt = half; mt < ntiles; mt += 2) {
+          const bool valid = (16 * mt + pos_in_tile) < a.n_m;
+#pragma unroll
+          for (int u = 0; u < UNITS; ++u) {
+            float v[16];
+            umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT + u * 16), v);
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int g = u * GPU_ + i / CG;
+                const float y = fmaf(v[i], a.acc_scale, s_par[u * 16 + i]);
+                if (pass == 0) s[g] += y;
+                else { const float d = y - mean[g]; s[g] = fmaf(d, d, s[g]); }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          s[g] += __shfl_xor_sync(0xffffffffu, s[g], 8);
+          s[g] += __shfl_xor_sync(0xffffffffu, s[g], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) s_red[pass][ew][row][g] = s[g];
+        }
+        pm_epi_barrier();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float t = 0.0f;
+#pragma unroll
+          for (int w = 0; w < kPmEpiWarps; ++w) t += s_red[pass][w][row][g];
+          if (pass == 0) mean[g] = t * inv_n;
+          else rstd[g] = rsqrtf(t * inv_n + 1e-5f);
+        }
+      }
+    }
+
+    const int n_acc = a.n_groups + a.aux;
+    const int rby_o = 2 * COUT;
+    for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
+      const bool is_aux = a.aux && g_acc == a.n_groups;
+      const float sc = is_aux ? a.aux_scale : a.acc_scale;
+      const float* pb = is_aux ? s_par + 256 : s_par;
+      void* o_hi = is_aux ? a.aux_hi : a.out_hi;
+      void* o_lo = is_aux ? a.aux_lo : a.out_lo;
+      for (int mt = half; mt < ntiles; mt += 2) {
+        const int idx = 16 * mt + pos_in_tile;
+        const bool valid = idx < a.n_m && grow < a.rows;
+        const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
+        float y[COUT];
+#pragma unroll
+        for (int u = 0; u < UNITS; ++u) {
+          float v[16];
+          umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT + u * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = fmaf(v[i], sc, pb[u * 16 + i]);
+            if (!is_aux && a.mode != PM_BIAS) {
+              const int g = u * GPU_ + i / CG;
+              t = (t - mean[g]) * rstd[g] * s_par[64 + u * 16 + i] + s_par[128 + u * 16 + i];
+              t = mish_fast(t) + s_par[192 + u * 16 + i];
+            }
+            y[u * 16 + i] = t;
+          }
+        }
+        if (!valid) continue;
+        const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
+        if (!is_aux && a.mode == PM_GN_RES) {
+          // out + x (blocks.py:164, identity residual): x = hi + lo of the block input, same layout
+#pragma unroll
+          for (int c = 0; c < COUT / 8; ++c) {
+            const size_t off = line + (size_t)(pm_swz(rby_o, row, c) << 4);
+            const uint4 h = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+            uint4 l = make_uint4(0, 0, 0, 0);
+            if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
+            float x[8];
+            tc_chunk_sum<EL>(h, l, a.res.lo != nullptr, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
+          }
+        }
+        if (o_hi) {
+#pragma unroll
+          for (int u = 0; u < UNITS; ++u) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = y[u * 16 + i];
+            uint4 h[4], l[4];
+            tc_split_store<EL>(v, o_lo != nullptr, h, l);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
+              *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
+              if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
+            }
+          }
+        }
+        if (!is_aux && a.tc_hi) {
+          // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
+          const int rt = grow / kTcRows, rl = grow % kTcRows;
+          const int kch = COUT / 64;
+#pragma unroll
+          for (int u = 0; u < UNITS; ++u) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = y[u * 16 + i];
+            uint4 h[4], l[4];
+            tc_split_store<EL>(v, a.tc_lo != nullptr, h, l);
+            const int k = lo * COUT + u * 16;
+            const size_t blk = ((size_t)rt * (a.lout * kch) + (k >> 6)) * kTcBlockBytes;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const size_t off = blk + tc_swz_bytes(rl, ((k & 63) >> 3) + m);
+              *reinterpret_cast<uint4*>((uint8_t*)a.tc_hi + off) = h[m];
+              if (a.tc_lo) *reinterpret_cast<uint4*>((uint8_t*)a.tc_lo + off) = l[m];
+            }
+          }
+        }
+        if (!is_aux && a.eps) {
+          // fused final nn.Conv1d(C, 7, 1) (temporalunet.py:36)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            float acc = s_fw[7 * COUT + j];
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc = fmaf(s_fw[j * COUT + c], y[c], acc);
+            a.eps[((size_t)grow * 7 + j) * a.lout + lo] = acc;
+          }
+        }
+      }
+    }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+  }
+}
+
+// x float32 [rows][7][50]  ->  position-major image with C = 16 (channels 7..15 zero), hi / lo halves.
+// One thread per (row, position).
+template <int EL>
+__global__ void pm_pack_input_kernel(const float* __restrict__ x, int rows, int L, void* __restrict__ hi,
+                                     void* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * L) return;
+  const int row = i / L, l = i % L;
+  float v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = e < kDof ? x[((size_t)row * kDof + e) * L + l] : 0.0f;
+  uint4 h[4], r[4];
+  tc_split_store<EL>(v, lo != nullptr, h, r);
+  const int rb = row / kPmRows, rr = row % kPmRows;
+  const size_t line = ((size_t)(rb * (L + 4) + l + 2) * 8 + rr) * 32;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const size_t off = line + (size_t)(pm_swz(32, rr, m) << 4);
+    *reinterpret_cast<uint4*>((uint8_t*)hi + off) = h[m];
+    if (lo) *reinterpret_cast<uint4*>((uint8_t*)lo + off) = r[m];
+  }
+}
+
+// position-major hi/lo -> plain [rows][C][L] (debug read-back for the per-layer parity taps)
+template <int EL>
+__global__ void pm_unpack_kernel(const void* __restrict__ hi, const void* __restrict__ lo, int rows, int C, int L,
+                                 float* __restrict__ x) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * C * L) return;
+  const int l = (int)(i % L), c = (int)((i / L) % C), row = (int)(i / ((size_t)C * L));
+  const int rb = row / kPmRows, rr = row % kPmRows, rby = 2 * C;
+  const size_t off = ((size_t)(rb * (L + 4) + l + 2) * 8 + rr) * rby + (size_t)(pm_swz(rby, rr, c >> 3) << 4) + (c & 7) * 2;
+  float v = unpack16x2<EL>((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)hi + off)).x;
+  if (lo) v += unpack16x2<EL>((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)lo + off)).x;
+  x[i] = v;
+}
+
+}  // namespace edmp

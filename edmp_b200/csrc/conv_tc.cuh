@@ -26,6 +26,7 @@
 // the 1x1 residual conv (second accumulator), stride-2 Conv1d (:211), ConvTranspose1d (:249).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -56,6 +57,7 @@ struct TcPhase {
   TcOperand a, b;       // b.C == 0 unless the input is a skip concat (blocks.py:253)
   const void* w_hi;     // packed weights [n_tile][c_chunk][slots * ct rows][128 B] swizzled
   const void* w_lo;
+  float acc_scale;      // exact inverse of the power-of-two weight scale (1 unless half operands)
   int lin;              // input positions
   int slots;            // slots stored per weight tile
   int d_col;            // accumulator column base
@@ -81,19 +83,21 @@ struct TcArgs {
   long long* dbg;               // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
 };
 
-// Element-type traits: TF32 operands are 4-byte floats (32 per 128-byte row), BF16 2-byte (64 per row)
-template <bool BF16> struct TcElem;
-template <> struct TcElem<false> {
+// Element-type traits: TF32 operands are 4-byte floats (32 per 128-byte row), BF16 / F16 2-byte (64 per row)
+enum TcEl { TC_EL_TF32 = 0, TC_EL_BF16 = 1, TC_EL_F16 = 2 };
+template <int EL> struct TcElem {
+  static constexpr bool k16 = true;
+  static constexpr int kCpc = 64;
+  static constexpr int kShift = 6;
+  static constexpr int kFmt = (EL == TC_EL_BF16) ? 1 : 0;   // UMMA a/b format: 1 = BF16, 0 = F16
+  static constexpr int kUnitChunks = 2;
+};
+template <> struct TcElem<TC_EL_TF32> {
+  static constexpr bool k16 = false;
   static constexpr int kCpc = 32;      // channels per K chunk
   static constexpr int kShift = 5;
   static constexpr int kFmt = 2;       // UMMA a/b format TF32
   static constexpr int kUnitChunks = 4;  // 16-byte chunks that 16 channels occupy
-};
-template <> struct TcElem<true> {
-  static constexpr int kCpc = 64;
-  static constexpr int kShift = 6;
-  static constexpr int kFmt = 1;       // BF16
-  static constexpr int kUnitChunks = 2;
 };
 
 // byte offset of 16-byte chunk `chunk16` of row `row_local` inside a tiled block
@@ -117,19 +121,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo_f(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// two 16-bit elements (BF16 or IEEE half) <-> two floats
+template <int EL> __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+  return EL == TC_EL_BF16 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+}
+template <int EL> __device__ __forceinline__ float2 unpack16x2(uint32_t v) {
+  if (EL == TC_EL_BF16) return make_float2(bf16_lo_f(v), bf16_hi_f(v));
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
 
 // split 16 fp32 values into hi/lo parts in the operand element type; writes kUnitChunks 16-byte chunks each
-template <bool BF16>
+template <int EL>
 __device__ __forceinline__ void tc_split_store(const float (&v)[16], bool want_lo, uint4* hi, uint4* lo) {
-  if (BF16) {
+  if (EL != TC_EL_TF32) {
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
       uint32_t h[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float x0 = v[m * 8 + 2 * e], x1 = v[m * 8 + 2 * e + 1];
-        h[e] = pack_bf16x2(x0, x1);
-        l[e] = want_lo ? pack_bf16x2(x0 - bf16_lo_f(h[e]), x1 - bf16_hi_f(h[e])) : 0u;
+        h[e] = pack16x2<EL>(x0, x1);
+        const float2 hf = unpack16x2<EL>(h[e]);
+        l[e] = want_lo ? pack16x2<EL>(x0 - hf.x, x1 - hf.y) : 0u;
       }
       hi[m] = make_uint4(h[0], h[1], h[2], h[3]);
       lo[m] = make_uint4(l[0], l[1], l[2], l[3]);
@@ -151,14 +168,15 @@ __device__ __forceinline__ void tc_split_store(const float (&v)[16], bool want_l
 }
 
 // sum of the hi and lo 16-byte chunks as fp32 values (4 for TF32, 8 for BF16)
-template <bool BF16>
+template <int EL>
 __device__ __forceinline__ void tc_chunk_sum(const uint4& h, const uint4& l, bool has_lo, float* out) {
   const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-  if (BF16) {
+  if (EL != TC_EL_TF32) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      out[2 * e] = bf16_lo_f(hh[e]) + (has_lo ? bf16_lo_f(ll[e]) : 0.0f);
-      out[2 * e + 1] = bf16_hi_f(hh[e]) + (has_lo ? bf16_hi_f(ll[e]) : 0.0f);
+      const float2 a = unpack16x2<EL>(hh[e]), b = unpack16x2<EL>(ll[e]);
+      out[2 * e] = a.x + (has_lo ? b.x : 0.0f);
+      out[2 * e + 1] = a.y + (has_lo ? b.y : 0.0f);
     }
   } else {
 #pragma unroll
@@ -166,9 +184,10 @@ __device__ __forceinline__ void tc_chunk_sum(const uint4& h, const uint4& l, boo
   }
 }
 
-template <bool BF16>
+template <int EL>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
-  using E = TcElem<BF16>;
+  using E = TcElem<EL>;
+  constexpr bool BF16 = E::k16;   // 16-bit operand elements (BF16 or IEEE half)
   constexpr int UC = E::kUnitChunks;           // 16-byte chunks per (row, 16-channel unit)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages] ... [barriers]; statically: parameters and GroupNorm partials
@@ -366,6 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
 
     float mean[2] = {0.0f, 0.0f}, rstd[2] = {1.0f, 1.0f};
+    const float sc0 = a.ph[0].acc_scale, sc1 = a.ph[1].acc_scale;   // exact power-of-two de-scaling of the weights
     if (a.mode != TC_BIAS) {
       // GroupNorm(8) over (cg channels x lout positions) of this row (blocks.py:24-26): two-pass,
       // partial sums of the column shares meet in shared memory
@@ -377,10 +397,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int c0 = (u * 16) % a.ct;
         if (gpt == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s[0] += v[i] + s_par[c0 + i];
+          for (int i = 0; i < 16; ++i) s[0] += fmaf(v[i], sc0, s_par[c0 + i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s[0] += v[i] + s_par[c0 + i]; s[1] += v[8 + i] + s_par[c0 + 8 + i]; }
+          for (int i = 0; i < 8; ++i) { s[0] += fmaf(v[i], sc0, s_par[c0 + i]); s[1] += fmaf(v[8 + i], sc0, s_par[c0 + 8 + i]); }
         }
       }
       s_stat[(part * 2 + 0) * 128 + row_local] = s[0];
@@ -400,12 +420,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int c0 = (u * 16) % a.ct;
         if (gpt == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float d = v[i] + s_par[c0 + i] - mean[0]; ss[0] = fmaf(d, d, ss[0]); }
+          for (int i = 0; i < 16; ++i) { const float d = fmaf(v[i], sc0, s_par[c0 + i]) - mean[0]; ss[0] = fmaf(d, d, ss[0]); }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float d0 = v[i] + s_par[c0 + i] - mean[0];
-            const float d1 = v[8 + i] + s_par[c0 + 8 + i] - mean[1];
+            const float d0 = fmaf(v[i], sc0, s_par[c0 + i]) - mean[0];
+            const float d1 = fmaf(v[8 + i], sc0, s_par[c0 + 8 + i]) - mean[1];
             ss[0] = fmaf(d0, d0, ss[0]);
             ss[1] = fmaf(d1, d1, ss[1]);
           }
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           uint4 l = make_uint4(0, 0, 0, 0);
           if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + src);
           float x[8];
-          tc_chunk_sum<BF16>(h, l, a.res.lo != nullptr, x);
+          tc_chunk_sum<EL>(h, l, a.res.lo != nullptr, x);
           // residual staging row: 16 floats = 4 x 16 B, chunk q at position q ^ ((r>>1)&3)
           float* dst = stg_res + (size_t)(uu * 128 + r) * 16;
           const int rs = (r >> 1) & 3;
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int c0 = (u * 16) % a.ct;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float y = v[i] + s_par[c0 + i];
+          float y = fmaf(v[i], sc0, s_par[c0 + i]);
           if (a.mode != TC_BIAS) {
             const bool g1 = (gpt == 2 && i >= 8);
             y = (y - (g1 ? mean[1] : mean[0])) * (g1 ? rstd[1] : rstd[0]) * s_par[64 + c0 + i] + s_par[128 + c0 + i];
@@ -485,7 +505,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           float r[16];
           umma::tmem_ld16(t_lane + a.ph[1].d_col + u * 16, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += r[i] + s_par[256 + c0 + i];
+          for (int i = 0; i < 16; ++i) v[i] += fmaf(r[i], sc1, s_par[256 + c0 + i]);
         } else if (a.mode == TC_GN_RES_ID) {
           const float* sr = stg_res + ((size_t)(u - u0) * 128 + row_local) * 16;
           const int rs = (row_local >> 1) & 3;
@@ -501,7 +521,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (a.out_hi) {
           // staging tile of this unit: [128 rows][UC x 16 B], chunk m of row r at position m ^ sw_out
           uint4 h[4], l[4];
-          tc_split_store<BF16>(v, a.out_lo != nullptr, h, l);
+          tc_split_store<EL>(v, a.out_lo != nullptr, h, l);
           uint4* sh = reinterpret_cast<uint4*>(stg_hi + ((size_t)(u - u0) * 128 + row_local) * (UC * 16));
           uint4* sl = reinterpret_cast<uint4*>(stg_lo + ((size_t)(u - u0) * 128 + row_local) * (UC * 16));
 #pragma unroll
@@ -558,10 +578,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
 // plain [rows][C][L] float32  ->  tiled hi/lo operand blocks (K order (l, c)); one thread per
 // (row, l, 16-byte chunk of channels)
-template <bool BF16>
+template <int EL>
 __global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int L, void* __restrict__ hi,
                                void* __restrict__ lo) {
-  using E = TcElem<BF16>;
+  using E = TcElem<EL>;
+  constexpr bool BF16 = E::k16;
   constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
   pdl_launch_dependents();
   pdl_wait();
@@ -582,16 +603,17 @@ __global__ void tc_pack_kernel(const float* __restrict__ x, int rows, int C, int
   const size_t blk = ((size_t)rt * (L * (C >> E::kShift)) + (k >> E::kShift)) * kTcBlockBytes;
   const int off = tc_swz_bytes(rl, (k & (E::kCpc - 1)) / EPC);
   uint4 h[4], r[4];
-  tc_split_store<BF16>(v, lo != nullptr, h, r);
+  tc_split_store<EL>(v, lo != nullptr, h, r);
   *reinterpret_cast<uint4*>((uint8_t*)hi + blk + off) = h[0];
   if (lo) *reinterpret_cast<uint4*>((uint8_t*)lo + blk + off) = r[0];
 }
 
 // tiled hi/lo -> plain [rows][C][L] (debug read-back)
-template <bool BF16>
+template <int EL>
 __global__ void tc_unpack_kernel(const void* __restrict__ hi, const void* __restrict__ lo, int rows, int C, int L,
                                  float* __restrict__ x) {
-  using E = TcElem<BF16>;
+  using E = TcElem<EL>;
+  constexpr bool BF16 = E::k16;
   constexpr int EPC = BF16 ? 8 : 4;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)rows * C * L;
@@ -606,8 +628,8 @@ __global__ void tc_unpack_kernel(const void* __restrict__ hi, const void* __rest
   const int e = k % EPC;
   if (BF16) {
     const uint16_t h = *reinterpret_cast<const uint16_t*>((const uint8_t*)hi + blk + off + e * 2);
-    float v = __uint_as_float((uint32_t)h << 16);
-    if (lo) v += __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)lo + blk + off + e * 2) << 16);
+    float v = unpack16x2<EL>((uint32_t)h).x;
+    if (lo) v += unpack16x2<EL>((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)lo + blk + off + e * 2)).x;
     x[i] = v;
   } else {
     float v = *reinterpret_cast<const float*>((const uint8_t*)hi + blk + off + e * 4);

@@ -220,8 +220,9 @@ struct UNet {
   int precision = 0;
   bool tc = false;        // tensor-core path for the L <= 7 levels
   bool tc_split = false;  // three-MMA hi/lo operand split
-  bool tc_bf16 = false;   // BF16 operand elements (else TF32)
-  int cpc() const { return tc_bf16 ? 64 : 32; }   // channels per 128-byte K chunk
+  int tc_el = TC_EL_TF32; // operand element type of the tensor path (TF32 / BF16 / IEEE half)
+  bool tc_16() const { return tc_el != TC_EL_TF32; }
+  int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   int max_rows = 0;
   int n_launches = 0;
@@ -395,14 +396,32 @@ struct Builder {
     std::memcpy(&r, &b, 4);
     return r;
   }
+  static uint16_t f16_round(float x) { return __half_as_ushort(__float2half_rn(x)); }   // RNE incl. subnormals
+  static float f16_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
   // Packs weights into UMMA-ready tiles [n_tile][c_chunk][slots*ct rows][128 B], SWIZZLE_128B,
   // K-major; wfn(co, ci, slot) supplies the value.  Produces the hi part and (split modes) the lo
   // remainder in the operand element type (TF32-rounded fp32 or BF16).
+  // IEEE-half operands: the weights are multiplied by a power of two `scale` (returned through
+  // acc_scale as its exact inverse) so that their lo parts stay in half's normal range; TF32 / BF16
+  // have fp32's exponent range and use scale 1.
   template <class F>
-  void pack_tc(int cout, int cin, int ct, int slots, F wfn, const void** hi_out, const void** lo_out) {
-    const int cpc = u->cpc(), ebytes = u->tc_bf16 ? 2 : 4, epc = 16 / ebytes;
+  void pack_tc(int cout, int cin, int ct, int slots, F wfn, const void** hi_out, const void** lo_out,
+               float* acc_scale) {
+    const int cpc = u->cpc(), ebytes = u->tc_16() ? 2 : 4, epc = 16 / ebytes;
     const int n_tiles = cout / ct, kch = cin / cpc;
+    float scale = 1.0f;
+    if (u->tc_el == TC_EL_F16) {
+      float wmax = 0.0f;
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int sl = 0; sl < slots; ++sl) wmax = std::max(wmax, std::fabs(wfn(co, ci, sl)));
+      int e = 0;
+      if (wmax > 0.0f) e = (int)std::floor(std::log2(16384.0f / wmax));   // |scale * w| <= 16384 < 65504
+      e = std::max(-8, std::min(24, e));
+      scale = std::ldexp(1.0f, e);
+    }
+    *acc_scale = 1.0f / scale;
     const size_t tile = (size_t)slots * ct * 128;   // bytes
     std::vector<uint8_t> hi(tile * n_tiles * kch), lo(u->tc_split ? hi.size() : 0);
     for (int nt = 0; nt < n_tiles; ++nt)
@@ -412,9 +431,16 @@ struct Builder {
           for (int c = 0; c < ct; ++c) {
             const int r = sl * ct + c;
             for (int e = 0; e < cpc; ++e) {
-              const float w = wfn(nt * ct + c, cc * cpc + e, sl);
+              const float w = scale * wfn(nt * ct + c, cc * cpc + e, sl);
               const size_t off = base + (size_t)r * 128 + ((((e / epc) ^ (r & 7)) << 4) | ((e % epc) * ebytes));
-              if (u->tc_bf16) {
+              if (u->tc_el == TC_EL_F16) {
+                const uint16_t h = f16_round(w);
+                std::memcpy(&hi[off], &h, 2);
+                if (u->tc_split) {
+                  const uint16_t l = f16_round(w - f16_to_float(h));
+                  std::memcpy(&lo[off], &l, 2);
+                }
+              } else if (u->tc_el == TC_EL_BF16) {
                 const uint16_t h = bf16_round(w);
                 std::memcpy(&hi[off], &h, 2);
                 if (u->tc_split) {
@@ -466,7 +492,7 @@ struct Builder {
       t.epi_units = (n_units + 3) & ~3;
     } else {
       // per 16-column unit: hi + lo output staging (128 rows x 64 B tf32 / 32 B bf16 each) + 8 KB residual
-      const size_t out_unit = (size_t)128 * (u->tc_bf16 ? 32 : 64) * 2;
+      const size_t out_unit = (size_t)128 * (u->tc_16() ? 32 : 64) * 2;
       const size_t per_unit = out_unit + (t.mode == TC_GN_RES_ID ? 8192 : 0);
       stage_total = std::max(stage_total, 4 * per_unit);
       const int cap = (int)(stage_total / per_unit);
@@ -516,7 +542,7 @@ struct Builder {
     const float* w = P(p + ".block.0.weight");   // [cout][cin][5]
     pack_tc(cout, cin, ct, ph.slots,
             [&](int co, int ci, int sl) { return w[((size_t)co * cin + ci) * 5 + (4 - (j_begin + sl))]; },
-            &ph.w_hi, &ph.w_lo);
+            &ph.w_hi, &ph.w_lo, &ph.acc_scale);
     t.bias = vec(p + ".block.0.bias", cout);
     t.gamma = vec(p + ".block.2.weight", cout);
     t.beta = vec(p + ".block.2.bias", cout);
@@ -534,7 +560,8 @@ struct Builder {
       pr.d_col = (L * ct <= 128) ? 128 : 256;
       for (int li = 0; li < L; ++li) { pr.sched[li].slot_begin = 0; pr.sched[li].n_slots = 1; pr.sched[li].lo_begin = (int8_t)li; }
       const float* wr = P(res_prefix + ".residual_conv.weight");   // [cout][rcin][1]
-      pack_tc(cout, rcin, ct, 1, [&](int co, int ci, int) { return wr[(size_t)co * rcin + ci]; }, &pr.w_hi, &pr.w_lo);
+      pack_tc(cout, rcin, ct, 1, [&](int co, int ci, int) { return wr[(size_t)co * rcin + ci]; }, &pr.w_hi, &pr.w_lo,
+              &pr.acc_scale);
       t.bres = vec(res_prefix + ".residual_conv.bias", cout);
       macs += (double)L * rcin * cout;
     }
@@ -592,7 +619,7 @@ struct Builder {
       }
       static const int tap_of_slot[3] = {2, 0, 1};
       pack_tc(C, C, ct, 3, [&](int co, int ci, int sl) { return w[((size_t)co * C + ci) * 3 + tap_of_slot[sl]]; },
-              &ph.w_hi, &ph.w_lo);
+              &ph.w_hi, &ph.w_lo, &ph.acc_scale);
     } else {
       // ConvTranspose1d(k=4, s=2, p=1): l_out = 2 l_in - 1 + tap; weight [cin][cout][4]
       ph.slots = 4;
@@ -605,7 +632,7 @@ struct Builder {
         ph.sched[li].lo_begin = (int8_t)(2 * li - 1 + tmin);
       }
       pack_tc(C, C, ct, 4, [&](int co, int ci, int sl) { return w[((size_t)ci * C + co) * 4 + sl]; }, &ph.w_hi,
-              &ph.w_lo);
+              &ph.w_lo, &ph.acc_scale);
     }
     t.bias = vec(name + ".bias", C);
     t.out_hi = y.thi;
@@ -660,8 +687,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   EDMP_REQUIRE(n_dims == 6 && dims[0] == 32 && dims[1] == 64 && dims[2] == 128 && dims[3] == 256 &&
                    dims[4] == 512 && dims[5] == 512,
                "only dims=(32,64,128,256,512,512) is compiled in (infer_serial.py:50)");
-  EDMP_REQUIRE(precision >= EDMP_PRECISION_FP32 && precision <= EDMP_PRECISION_BF16,
-               "precision must be one of fp32, tf32x3, tf32, bf16x3, bf16");
+  EDMP_REQUIRE(precision >= EDMP_PRECISION_FP32 && precision <= EDMP_PRECISION_F16,
+               "precision must be one of fp32, tf32x3, tf32, bf16x3, bf16, f16x3, f16");
   EDMP_REQUIRE(max_rows > 0, "max_rows must be positive");
   ParamWalker pw;
   walk_params(dims, n_dims, pw);
@@ -671,13 +698,16 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->precision = precision;
   u->max_rows = max_rows;
   u->tc = precision != EDMP_PRECISION_FP32;
-  u->tc_split = precision == EDMP_PRECISION_TF32X3 || precision == EDMP_PRECISION_BF16X3;
-  u->tc_bf16 = precision == EDMP_PRECISION_BF16X3 || precision == EDMP_PRECISION_BF16;
+  u->tc_split = precision == EDMP_PRECISION_TF32X3 || precision == EDMP_PRECISION_BF16X3 ||
+                precision == EDMP_PRECISION_F16X3;
+  u->tc_el = (precision == EDMP_PRECISION_BF16X3 || precision == EDMP_PRECISION_BF16) ? TC_EL_BF16
+             : (precision == EDMP_PRECISION_F16X3 || precision == EDMP_PRECISION_F16) ? TC_EL_F16 : TC_EL_TF32;
   if (u->tc) {
     static bool attr_set = false;
     if (!attr_set) {
-      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       attr_set = true;
     }
   }
@@ -793,17 +823,16 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
     dim3 grid((rows + kTcRows - 1) / kTcRows, ly.tc_tiles);
-    if (u->tc_bf16) launch_pdl(conv_tc_kernel<true>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
-    else launch_pdl(conv_tc_kernel<false>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
+    if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc_kernel<TC_EL_F16>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
+    else if (u->tc_el == TC_EL_BF16) launch_pdl(conv_tc_kernel<TC_EL_BF16>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
+    else launch_pdl(conv_tc_kernel<TC_EL_TF32>, grid, dim3(kTcThreads), ly.tc_smem, st, a);
   } else {
-    const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / (u->tc_bf16 ? 8 : 4));
+    const size_t total = (size_t)rows * ly.pack_src.L * (ly.pack_src.C / (u->tc_16() ? 8 : 4));
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (u->tc_bf16)
-      launch_pdl(tc_pack_kernel<true>, dim3(blocks), dim3(256), 0, st, (const float*)ly.pack_src.p, rows, ly.pack_src.C,
-                 ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
-    else
-      launch_pdl(tc_pack_kernel<false>, dim3(blocks), dim3(256), 0, st, (const float*)ly.pack_src.p, rows, ly.pack_src.C,
-                 ly.pack_src.L, ly.pack_dst.thi, ly.pack_dst.tlo);
+    auto pack = u->tc_el == TC_EL_F16 ? tc_pack_kernel<TC_EL_F16>
+                : u->tc_el == TC_EL_BF16 ? tc_pack_kernel<TC_EL_BF16> : tc_pack_kernel<TC_EL_TF32>;
+    launch_pdl(pack, dim3(blocks), dim3(256), 0, st, (const float*)ly.pack_src.p, rows, ly.pack_src.C, ly.pack_src.L,
+               ly.pack_dst.thi, ly.pack_dst.tlo);
   }
 }
 
@@ -894,8 +923,9 @@ int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C
     if (a.p) {
       EDMP_CK(cudaMemcpyAsync(out, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-      if (u->tc_bf16) tc_unpack_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
-      else tc_unpack_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
+      auto unpack = u->tc_el == TC_EL_F16 ? tc_unpack_kernel<TC_EL_F16>
+                    : u->tc_el == TC_EL_BF16 ? tc_unpack_kernel<TC_EL_BF16> : tc_unpack_kernel<TC_EL_TF32>;
+      unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.thi, a.tlo, rows, a.C, a.L, out);
       EDMP_CK(cudaGetLastError());
     }
   }

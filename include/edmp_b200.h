@@ -47,7 +47,10 @@ enum {
   EDMP_PRECISION_TF32X3 = 1,  /* tcgen05 kind::tf32 with hi/lo operand split (3 MMAs, ~fp32)     */
   EDMP_PRECISION_TF32 = 2,    /* tcgen05 kind::tf32 single pass (fast, ~1e-3 relative)           */
   EDMP_PRECISION_BF16X3 = 3,  /* tcgen05 kind::f16 bf16 hi/lo split (3 MMAs, ~2^-16 relative)    */
-  EDMP_PRECISION_BF16 = 4     /* tcgen05 kind::f16 bf16 single pass (fastest, ~1e-2 relative)    */
+  EDMP_PRECISION_BF16 = 4,    /* tcgen05 kind::f16 bf16 single pass (fastest, ~1e-2 relative)    */
+  EDMP_PRECISION_F16X3 = 5,   /* tcgen05 kind::f16 IEEE-half hi/lo split with power-of-two weight
+                                 scaling (3 MMAs at twice the tf32 rate, ~fp32; parity grade)     */
+  EDMP_PRECISION_F16 = 6      /* tcgen05 kind::f16 IEEE-half single pass (~1e-3 relative)          */
 };
 
 const char* edmp_last_error(void);

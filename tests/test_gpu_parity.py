@@ -14,14 +14,14 @@ DEV = "cuda:0"
 DIMS = (32, 64, 128, 256, 512, 512)
 
 
-PRECISIONS = os.environ.get("EDMP_TEST_PRECISIONS", "fp32,tf32x3,bf16x3").split(",")
+PRECISIONS = os.environ.get("EDMP_TEST_PRECISIONS", "fp32,tf32x3,f16x3").split(",")
 # max |eps - reference| allowed per arithmetic mode (eps is O(1)): fp32 FMA = summation-order noise;
-# 3xTF32 / 3xBF16 = operand split error + the tensor core's truncating fp32 accumulation
-EPS_TOL = {"fp32": 2e-5, "tf32x3": 2e-5, "bf16x3": 5e-5}
+# 3xTF32 / 3xF16 / 3xBF16 = operand split error + the tensor core's truncating fp32 accumulation
+EPS_TOL = {"fp32": 2e-5, "tf32x3": 2e-5, "f16x3": 2e-5, "bf16x3": 5e-5}
 # full 255-step trajectories against the reference's: the north-star bar is 1e-4 rad.  fp32 and
-# 3xTF32 are held to it; 3xBF16 (per-step eps error ~40x fp32) is a throughput mode and only held to
+# 3xTF32 / 3xF16 are held to it; 3xBF16 (per-step eps error ~40x fp32) is a throughput mode and only held to
 # 1e-3 on these fixtures, whose guided chain amplifies perturbations (DESIGN.md "conditioning").
-E2E_TOL = {"fp32": 1e-4, "tf32x3": 1e-4, "bf16x3": 5e-2}
+E2E_TOL = {"fp32": 1e-4, "tf32x3": 1e-4, "f16x3": 1e-4, "bf16x3": 5e-2}
 
 
 def _model(tmp_path_factory, sd, precision="fp32"):
@@ -77,7 +77,7 @@ def test_unet_matches_reference_fixture(golden, model):
                     assert act.shape == ref.shape
                     # fp32 FMA path: accumulation-order noise only.  3xTF32: the tensor core's fp32
                     # accumulator truncates on every MMA, ~3e-6 relative per layer.
-                    tol = {"fp32": 2e-5, "tf32x3": 6e-5, "bf16x3": 1.2e-4}[model.precision]
+                    tol = {"fp32": 2e-5, "tf32x3": 6e-5, "f16x3": 6e-5, "bf16x3": 1.2e-4}[model.precision]
                     assert np.abs(act - ref).max() <= tol * max(1.0, np.abs(ref).max()), name
 
 
