@@ -80,11 +80,6 @@ struct PmArgs {
   int rows;
 };
 
-// swizzle of 16-byte chunk `c` in row `r` of an atom with `rby`-byte rows (rby = 32 / 64 / 128)
-__device__ __forceinline__ int pm_swz(int rby, int r, int c) {
-  return rby == 128 ? (c ^ (r & 7)) : (rby == 64 ? (c ^ ((r >> 1) & 3)) : (c ^ ((r >> 2) & 1)));
-}
-
 __device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, int rby) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);

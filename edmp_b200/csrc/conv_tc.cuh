@@ -79,6 +79,7 @@ struct TcArgs {
   const float *bias, *gamma, *beta, *temb, *bres;
   TcOperand res;                // identity residual source (tiled)
   void *out_hi, *out_lo;        // tiled output, may be null
+  int out_pm;                   // 1: out_hi/out_lo are position-major images (conv_pm.cuh) of (cout, lout)
   float* out_plain;             // plain [rows][cout][lout], may be null
   long long* dbg;               // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
 };
@@ -103,6 +104,11 @@ template <> struct TcElem<TC_EL_TF32> {
 // byte offset of 16-byte chunk `chunk16` of row `row_local` inside a tiled block
 __device__ __forceinline__ int tc_swz_bytes(int row_local, int chunk16) {
   return row_local * 128 + ((chunk16 ^ (row_local & 7)) << 4);
+}
+
+// swizzle of 16-byte chunk `c` in row `r` of a position-major atom with `rby`-byte rows (32 / 64 / 128)
+__device__ __forceinline__ int pm_swz(int rby, int r, int c) {
+  return rby == 128 ? (c ^ (r & 7)) : (rby == 64 ? (c ^ ((r >> 1) & 3)) : (c ^ ((r >> 2) & 1)));
 }
 
 // Mish with hardware exp2 / reciprocal approximations (rel. error ~1e-6, below the split-MMA
@@ -546,7 +552,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const int lo = (u * 16) / a.ct;
           const int k = lo * a.cout + nt * a.ct + (u * 16) % a.ct;
           const int chunk = (((k & (E::kCpc - 1)) * (BF16 ? 2 : 4)) >> 4) + m;
-          const size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(r, chunk);
+          size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(r, chunk);
+          if (BF16 && a.out_pm) {
+            // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
+            const int grow = rt * kTcRows + r, rby = 2 * a.cout;
+            const int c = nt * a.ct + (u * 16) % a.ct;
+            dst = ((size_t)((grow >> 3) * (a.lout + 4) + lo + 2) * 8 + (grow & 7)) * rby +
+                  (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
+          }
           const int sw = (UC == 4) ? ((r >> 1) & 3) : ((r >> 2) & 1);
           const size_t src = ((size_t)(uu * 128 + r) * UC + (m ^ sw)) * 16;
           *reinterpret_cast<uint4*>((uint8_t*)a.out_hi + dst) = *reinterpret_cast<const uint4*>(stg_hi + src);

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_pm.cuh"
 #include "edmp_b200.h"
 
 namespace edmp {
@@ -185,18 +186,21 @@ size_t unet_param_count(const int* dims, int n_dims) {
 // ---- engine -----------------------------------------------------------------------------------------
 struct Act {
   float* p = nullptr;              // plain [rows][C][L] float32 (CUDA-core layers), may be null
-  void *thi = nullptr, *tlo = nullptr;   // tiled hi / lo operand blocks (tensor-core layers)
+  void *thi = nullptr, *tlo = nullptr;   // tiled hi / lo operand blocks (rows-as-M tensor-core layers)
+  void *phi = nullptr, *plo = nullptr;   // position-major hi / lo images (conv_pm.cuh)
   int C = 0, L = 0;
   bool ok = true;
 };
 
-enum LayerKind { LAYER_SIMT = 0, LAYER_TC = 1, LAYER_PACK = 2 };
+enum LayerKind { LAYER_SIMT = 0, LAYER_TC = 1, LAYER_PACK = 2, LAYER_PM = 3, LAYER_PM_PACK = 4 };
 
 struct Layer {
   int kind = LAYER_SIMT;
   ConvLaunchFn fn = nullptr;
   ConvArgs args;
   TcArgs targs;                 // LAYER_TC
+  PmArgs pargs;                 // LAYER_PM
+  bool pm_final = false;        // LAYER_PM: writes eps (the caller's buffer) through the fused final 1x1 conv
   int tc_tiles = 0;             // column tiles (grid.y) of a tensor-core layer
   size_t tc_smem = 0;
   Act pack_src, pack_dst;       // LAYER_PACK
@@ -222,6 +226,8 @@ struct UNet {
   bool tc_split = false;  // three-MMA hi/lo operand split
   int tc_el = TC_EL_TF32; // operand element type of the tensor path (TF32 / BF16 / IEEE half)
   bool tc_16() const { return tc_el != TC_EL_TF32; }
+  bool pm = false;        // position-major tensor-core kernels for the horizon 25 / 50 levels (16-bit elements)
+  bool final_fused = false;   // final 1x1 conv fused into the last position-major layer
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   int max_rows = 0;
@@ -251,10 +257,22 @@ static float* upload(UNet* u, const std::vector<float>& v) {
   return static_cast<float*>(upload_bytes(u, v.data(), v.size() * sizeof(float)));
 }
 
-static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = true, bool tiled = false) {
+static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = true, bool tiled = false,
+                   bool pm = false) {
   Act a;
   a.C = C; a.L = L;
   bool ok = true;
+  if (pm) {
+    // [row block of 8][L + 4 positions][8 rows][C halves]; zero-filled once: the halo positions and the
+    // padding rows of the last block are never written and must stay zero / finite
+    const size_t n = (size_t)((u->max_rows + kPmRows - 1) / kPmRows) * (L + 4) * 16 * C;
+    ok = cudaMalloc(&a.phi, n) == cudaSuccess;
+    if (ok) { u->dev_allocs.push_back(a.phi); cudaMemset(a.phi, 0, n); }
+    if (ok && u->tc_split) {
+      ok = cudaMalloc(&a.plo, n) == cudaSuccess;
+      if (ok) { u->dev_allocs.push_back(a.plo); cudaMemset(a.plo, 0, n); }
+    }
+  }
   if (plain) {
     ok = cudaMalloc(&a.p, (size_t)u->max_rows * C * L * sizeof(float)) == cudaSuccess;
     if (ok) u->dev_allocs.push_back(a.p);
@@ -269,7 +287,7 @@ static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = 
       if (ok) { u->dev_allocs.push_back(a.tlo); cudaMemset(a.tlo, 0, n); }
     }
   }
-  if (!ok) { a.p = nullptr; a.thi = nullptr; a.ok = false; return a; }
+  if (!ok) { a.p = nullptr; a.thi = nullptr; a.phi = nullptr; a.ok = false; return a; }
   if (!name.empty()) u->acts[name] = a;
   return a;
 }
@@ -584,11 +602,11 @@ struct Builder {
   }
 
   // stride-2 Conv1d / ConvTranspose1d on tensor cores (tiled in; tiled and/or plain out)
-  Act tc_resample(const std::string& name, const Act& x, bool up, bool plain_out) {
+  Act tc_resample(const std::string& name, const Act& x, bool up, bool plain_out, bool pm_out = false) {
     const int C = x.C, L = x.L;
     const int lout = up ? ((2 * L == 8 || 2 * L == 14 || 2 * L == 26) ? 2 * L - 1 : 2 * L) : (L + 1) / 2;
     const int ct = std::max(16, C / 8);
-    Act y = new_act(u, name, C, lout, plain_out, !plain_out);
+    Act y = new_act(u, name, C, lout, plain_out, !plain_out && !pm_out, pm_out);
     ok = ok && y.ok;
     Layer ly;
     std::memset(&ly.args, 0, sizeof(ConvArgs));
@@ -635,12 +653,236 @@ struct Builder {
               &ph.w_lo, &ph.acc_scale);
     }
     t.bias = vec(name + ".bias", C);
-    t.out_hi = y.thi;
-    t.out_lo = y.tlo;
+    t.out_hi = pm_out ? y.phi : y.thi;
+    t.out_lo = pm_out ? y.plo : y.tlo;
+    t.out_pm = pm_out ? 1 : 0;
     t.out_plain = y.p;
     ly.name = name;
     ly.macs_per_row = (up ? count_pairs<OP_UP4>(L, lout) : count_pairs<OP_DOWN3>(L, lout)) * C * C;
     finish_tc_layer(ly, C / ct);
+    u->layers.push_back(ly);
+    return y;
+  }
+
+
+  // ---------------- position-major tensor-core layers (conv_pm.cuh), horizon 25 / 50 ----------------
+  static PmAct pm_operand(const Act* a) {
+    PmAct o;
+    o.hi = a ? a->phi : nullptr;
+    o.lo = a ? a->plo : nullptr;
+    o.C = a ? a->C : 0;
+    return o;
+  }
+
+  // 16-bit element encode of (scaled) weight w into hi / lo
+  void encode16(float w, uint16_t* h, uint16_t* l) const {
+    if (u->tc_el == TC_EL_F16) {
+      *h = f16_round(w);
+      *l = f16_round(w - f16_to_float(*h));
+    } else {
+      *h = bf16_round(w);
+      *l = bf16_round(w - bf16_to_float(*h));
+    }
+  }
+
+  // weights of one slot group into [slot][k chunk][cout rows][2C bytes] swizzled images (hi, lo);
+  // wfn(co, ci, slot).  Returns the exact inverse of the power-of-two scale.
+  template <class F>
+  float pack_pm_slots(std::vector<uint8_t>& hi, std::vector<uint8_t>& lo, int slot0, int n_slots, int cout, int C,
+                      int nkc, F wfn) {
+    const int rby = 2 * C;
+    float scale = 1.0f;
+    if (u->tc_el == TC_EL_F16) {
+      float wmax = 0.0f;
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < C * nkc; ++ci)
+          for (int sl = 0; sl < n_slots; ++sl) wmax = std::max(wmax, std::fabs(wfn(co, ci, sl)));
+      int e = 0;
+      if (wmax > 0.0f) e = (int)std::floor(std::log2(16384.0f / wmax));
+      e = std::max(-8, std::min(24, e));
+      scale = std::ldexp(1.0f, e);
+    }
+    for (int sl = 0; sl < n_slots; ++sl)
+      for (int kc = 0; kc < nkc; ++kc)
+        for (int co = 0; co < cout; ++co)
+          for (int c = 0; c < C; ++c) {
+            const float w = scale * wfn(co, kc * C + c, sl);
+            const int r8 = co & 7, chunk = (c * 2) >> 4;
+            const int sw = rby == 128 ? (chunk ^ r8) : (rby == 64 ? (chunk ^ ((r8 >> 1) & 3)) : (chunk ^ ((r8 >> 2) & 1)));
+            const size_t off = ((size_t)((slot0 + sl) * nkc + kc) * cout + co) * rby + (size_t)(sw << 4) + ((c * 2) & 15);
+            uint16_t h, l;
+            encode16(w, &h, &l);
+            std::memcpy(&hi[off], &h, 2);
+            std::memcpy(&lo[off], &l, 2);
+          }
+    return 1.0f / scale;
+  }
+
+  void finish_pm_layer(Layer& ly, int atoms_needed, int n_slots) {
+    PmArgs& t = ly.pargs;
+    const int C = t.a.C, rby = 2 * C, atom = 8 * rby;
+    const int nkc = t.b.C ? 2 : 1, nparts = u->tc_split ? 2 : 1;
+    t.split = u->tc_split ? 1 : 0;
+    t.a_bytes_img = (t.lin + 4) * atom;
+    const int nimg = nkc * nparts;
+    t.a_bytes_total = nimg * t.a_bytes_img;
+    t.w_bytes_part = n_slots * nkc * t.cout * rby;
+    // the last M tile reads (finite garbage) past the last image: that tail may overlap the weights
+    const size_t tail_end = (size_t)(nimg - 1) * t.a_bytes_img + (size_t)atoms_needed * atom;
+    const int ntiles = (t.n_m + 15) / 16;
+    int cols = (t.n_groups + t.aux) * ntiles * t.cout, p2 = 32;
+    while (p2 < cols) p2 *= 2;
+    t.tmem_cols = p2;
+    ok = ok && p2 <= 512;
+    ly.kind = LAYER_PM;
+    ly.tc_smem = 1024 + std::max((((size_t)t.a_bytes_total + 1023) & ~(size_t)1023) + (size_t)nparts * t.w_bytes_part,
+                                 tail_end) + 256;
+    ok = ok && ly.tc_smem <= 232448 - 9216 - 1024;
+  }
+
+  // Conv1dBlock (conv5 + GroupNorm + Mish [+ time embedding] [+ identity residual]) on the
+  // position-major kernel.  aux_prefix != "": also emit the block's 1x1 residual conv of the input.
+  Act pm_conv_block(const std::string& p, const Act& xa, const Act* xb, int cout, const std::string& out_name,
+                    int temb_off, const Act* res, const std::string& aux_prefix, Act* aux_out, bool final_layer) {
+    const int C = xa.C, nkc = xb ? 2 : 1, cin = C * nkc, L = xa.L;
+    ok = ok && (!xb || xb->C == C) && (cout == 32 || cout == 64) && (C == 16 || C == 32 || C == 64);
+    // (the final block's activation is also kept: it is one of the per-layer parity taps)
+    Act y = new_act(u, out_name, cout, L, false, false, true);
+    ok = ok && y.ok;
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    std::memset(&ly.pargs, 0, sizeof(PmArgs));
+    PmArgs& t = ly.pargs;
+    t.a = pm_operand(&xa);
+    t.b = pm_operand(xb);
+    t.lin = L; t.n_m = L; t.lout = L; t.stride = 1;
+    t.n_terms = 5;
+    for (int j = 0; j < 5; ++j) { t.terms[j].acc = 0; t.terms[j].slot = (int8_t)j; t.terms[j].off = (int8_t)j; }
+    t.n_groups = 1; t.out_step = 1; t.out_off[0] = 0; t.out_off[1] = 0;
+    t.cout = cout;
+    t.mode = res ? PM_GN_RES : PM_GN;
+    const bool aux = !aux_prefix.empty();
+    const int n_slots = aux ? 6 : 5;
+    const int rby = 2 * C;
+    std::vector<uint8_t> hi((size_t)n_slots * nkc * cout * rby), lo(hi.size());
+    const float* w = P(p + ".block.0.weight");   // [cout][cin_real][5]; the packed input has C >= cin_real channels
+    const int cin_real = pw->table.at(p + ".block.0.weight").d1;
+    t.acc_scale = pack_pm_slots(hi, lo, 0, 5, cout, C, nkc, [&](int co, int ci, int sl) {
+      return ci < cin_real ? w[((size_t)co * cin_real + ci) * 5 + sl] : 0.0f;
+    });
+    if (aux) {
+      const float* wr = P(aux_prefix + ".residual_conv.weight");   // [cout][cin_real][1]
+      t.aux = 1;
+      t.terms[5].acc = 1; t.terms[5].slot = 5; t.terms[5].off = 2;
+      t.n_terms = 6;
+      t.aux_scale = pack_pm_slots(hi, lo, 5, 1, cout, C, nkc, [&](int co, int ci, int) {
+        return ci < cin_real ? wr[(size_t)co * cin_real + ci] : 0.0f;
+      });
+      t.aux_bias = vec(aux_prefix + ".residual_conv.bias", cout);
+      *aux_out = new_act(u, aux_prefix + ".residual_conv", cout, L, false, false, true);
+      ok = ok && aux_out->ok;
+      t.aux_hi = aux_out->phi;
+      t.aux_lo = aux_out->plo;
+    }
+    (void)cin;
+    t.w_hi = upload_bytes(u, hi.data(), hi.size());
+    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size()) : nullptr;
+    ok = ok && t.w_hi && (!u->tc_split || t.w_lo);
+    t.bias = vec(p + ".block.0.bias", cout);
+    t.gamma = vec(p + ".block.2.weight", cout);
+    t.beta = vec(p + ".block.2.bias", cout);
+    if (res) t.res = pm_operand(res);
+    t.out_hi = y.phi;
+    t.out_lo = y.plo;
+    if (final_layer) {
+      t.fw = vec("final_conv.1.weight", kDof * cout);
+      t.fb = vec("final_conv.1.bias", kDof);
+      ly.pm_final = true;
+    }
+    ly.temb_off = temb_off;
+    ly.name = p;
+    ly.macs_per_row = count_pairs<OP_CONV5>(L, L) * cin_real * cout + (aux ? (double)L * cin_real * cout : 0.0) +
+                      (final_layer ? (double)L * cout * kDof : 0.0);
+    const int ntiles = (L + 15) / 16;
+    finish_pm_layer(ly, 16 * ntiles + 4, n_slots);
+    u->layers.push_back(ly);
+    return y;
+  }
+
+  // ResidualConvolutionBlock (blocks.py:154-166): blocks.0 also emits the 1x1 residual conv of the block
+  // input when C_in != C_out, blocks.1 adds it (or the block input itself) as an identity residual
+  Act pm_res_block(const std::string& p, const Act& xa, const Act* xb, int cout, int cin_real) {
+    const int off = temb_width;
+    temb_blocks.push_back({p, off});
+    temb_width += cout;
+    const bool proj = cin_real != cout;
+    Act aux;
+    Act h = pm_conv_block(p + ".blocks.0", xa, xb, cout, p + ".blocks.0", off, nullptr, proj ? p : "", &aux, false);
+    return pm_conv_block(p + ".blocks.1", h, nullptr, cout, p, -1, proj ? &aux : &xa, "", nullptr, false);
+  }
+
+  // stride-2 Conv1d (blocks.py:211) / ConvTranspose1d (:249) on the position-major kernel; tc_out:
+  // write the rows-as-M tiles of conv_tc.cuh (the 25 -> 13 hand-over to the deep levels)
+  Act pm_resample(const std::string& name, const Act& x, bool up, bool tc_out) {
+    const int C = x.C, L = x.L;
+    const int lout = up ? 2 * L : (L + 1) / 2;
+    Act y = new_act(u, name, C, lout, false, tc_out, !tc_out);
+    ok = ok && y.ok && (C == 32 || C == 64);
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    std::memset(&ly.pargs, 0, sizeof(PmArgs));
+    PmArgs& t = ly.pargs;
+    t.a = pm_operand(&x);
+    t.b = pm_operand(nullptr);
+    t.lin = L; t.lout = lout; t.cout = C; t.mode = PM_BIAS;
+    const int rby = 2 * C;
+    const float* w = P(name + ".weight");
+    int atoms_needed, n_slots;
+    if (!up) {
+      // l_in = 2 l_out + tap - 1  ->  padded atom 2 l_out + tap + 1, stride 2
+      t.n_m = lout; t.stride = 2; t.n_groups = 1; t.out_step = 1;
+      t.n_terms = 3; n_slots = 3;
+      for (int j = 0; j < 3; ++j) { t.terms[j].acc = 0; t.terms[j].slot = (int8_t)j; t.terms[j].off = (int8_t)(j + 1); }
+      atoms_needed = 32 * ((lout + 15) / 16) + 2;
+    } else {
+      // l_out = 2 l_in - 1 + tap: even outputs 2m <- taps 1 (l_in = m), 3 (m - 1); odd 2m+1 <- taps 0 (m + 1), 2 (m)
+      t.n_m = L; t.stride = 1; t.n_groups = 2; t.out_step = 2; t.out_off[0] = 0; t.out_off[1] = 1;
+      t.n_terms = 4; n_slots = 4;
+      const int8_t acc[4] = {0, 0, 1, 1}, slot[4] = {1, 3, 0, 2}, off[4] = {2, 1, 3, 2};
+      for (int j = 0; j < 4; ++j) { t.terms[j].acc = acc[j]; t.terms[j].slot = slot[j]; t.terms[j].off = off[j]; }
+      atoms_needed = 16 * ((L + 15) / 16) + 4;
+    }
+    std::vector<uint8_t> hi((size_t)n_slots * C * rby), lo(hi.size());
+    t.acc_scale = pack_pm_slots(hi, lo, 0, n_slots, C, C, 1, [&](int co, int ci, int sl) {
+      return up ? w[((size_t)ci * C + co) * 4 + sl] : w[((size_t)co * C + ci) * 3 + sl];
+    });
+    t.w_hi = upload_bytes(u, hi.data(), hi.size());
+    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size()) : nullptr;
+    ok = ok && t.w_hi && (!u->tc_split || t.w_lo);
+    t.bias = vec(name + ".bias", C);
+    if (tc_out) { t.tc_hi = y.thi; t.tc_lo = y.tlo; }
+    else { t.out_hi = y.phi; t.out_lo = y.plo; }
+    ly.name = name;
+    ly.macs_per_row = (up ? count_pairs<OP_UP4>(L, lout) : count_pairs<OP_DOWN3>(L, lout)) * C * C;
+    finish_pm_layer(ly, atoms_needed, n_slots);
+    u->layers.push_back(ly);
+    return y;
+  }
+
+  // caller's x float32 [rows][7][50] -> position-major image, 16 channels (7 real)
+  Act pm_pack_input(const Act& x) {
+    Act y = new_act(u, "", 16, x.L, false, false, true);
+    ok = ok && y.ok;
+    Layer ly;
+    std::memset(&ly.args, 0, sizeof(ConvArgs));
+    std::memset(&ly.targs, 0, sizeof(TcArgs));
+    std::memset(&ly.pargs, 0, sizeof(PmArgs));
+    ly.kind = LAYER_PM_PACK;
+    ly.pack_src = x;
+    ly.pack_dst = y;
+    ly.name = "input (position-major pack)";
     u->layers.push_back(ly);
     return y;
   }
@@ -708,6 +950,10 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
       attr_set = true;
     }
   }
@@ -719,11 +965,22 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   b.ok = b.ok && x.p;
   std::vector<Act> skips;
   const int n_down = (int)d.size() - 1;
-  // Levels with horizon <= 13 (94 % of the MACs) run on tensor cores when precision != fp32; the
-  // long-horizon, few-channel levels stay on the CUDA-core kernels.
+  // Levels with horizon <= 13 (94 % of the MACs) run on the rows-as-M tensor-core kernel when
+  // precision != fp32; the long-horizon, few-channel levels run on the position-major tensor-core
+  // kernel when the operand elements are 16-bit, else on the CUDA-core kernels.
+  u->pm = u->tc && u->tc_16() && getenv("EDMP_NO_PM") == nullptr;
   auto on_tc = [&](const Act& a) { return u->tc && a.L <= kTcMaxLin; };
+  auto on_pm = [&](const Act& a) { return u->pm && a.L > kTcMaxLin; };
+  if (u->pm) x = b.pm_pack_input(x);
   for (int i = 0; i < n_down; ++i) {
     const std::string p = "down_samplers." + std::to_string(i) + ".down.";
+    if (on_pm(x)) {
+      x = b.pm_res_block(p + "0", x, nullptr, d[i + 1], d[i]);
+      x = b.pm_res_block(p + "1", x, nullptr, d[i + 1], d[i + 1]);
+      skips.push_back(x);
+      x = b.pm_resample(p + "3", x, false, /*tc_out=*/(x.L + 1) / 2 <= kTcMaxLin);
+      continue;
+    }
     if (on_tc(x)) {
       if (!x.thi) x = b.pack_to_tiled(x, p + "0");
       x = b.tc_res_block(p + "0", x, nullptr, d[i + 1]);
@@ -747,23 +1004,32 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
     const std::string p = "up_samplers." + std::to_string(n) + ".up.";
     Act h = skips.back();
     skips.pop_back();
-    if (on_tc(x)) {
+    if (on_pm(x)) {
+      x = b.pm_res_block(p + "0", x, &h, d[i - 1], 2 * d[i]);
+      x = b.pm_res_block(p + "1", x, nullptr, d[i - 1], d[i - 1]);
+      x = b.pm_resample(p + "3", x, true, false);
+    } else if (on_tc(x)) {
       x = b.tc_res_block(p + "0", x, &h, d[i - 1]);
       x = b.tc_res_block(p + "1", x, nullptr, d[i - 1]);
-      // the up-sampled output feeds a CUDA-core level when it is longer than 13
+      // the up-sampled output feeds a position-major / CUDA-core level when it is longer than 13
       const int lup = (2 * x.L == 8 || 2 * x.L == 14 || 2 * x.L == 26) ? 2 * x.L - 1 : 2 * x.L;
-      x = b.tc_resample(p + "3", x, true, /*plain_out=*/lup > kTcMaxLin);
+      x = b.tc_resample(p + "3", x, true, /*plain_out=*/lup > kTcMaxLin && !u->pm, /*pm_out=*/lup > kTcMaxLin && u->pm);
     } else {
       x = b.res_block(p + "0", x, &h, d[i - 1]);
       x = b.res_block(p + "1", x, nullptr, d[i - 1]);
       x = b.resample(p + "3", x, true);
     }
   }
-  x = b.conv_block("final_conv.0", x, nullptr, d[1], "final_conv.0", -1, 0, nullptr, nullptr, "");
-  u->final_in = x;
-  u->final_c = d[1];
-  u->final_w = b.vec("final_conv.1.weight", kDof * d[1]);
-  u->final_b = b.vec("final_conv.1.bias", kDof);
+  if (on_pm(x)) {
+    b.pm_conv_block("final_conv.0", x, nullptr, d[1], "final_conv.0", -1, nullptr, "", nullptr, /*final_layer=*/true);
+    u->final_fused = true;
+  } else {
+    x = b.conv_block("final_conv.0", x, nullptr, d[1], "final_conv.0", -1, 0, nullptr, nullptr, "");
+    u->final_in = x;
+    u->final_c = d[1];
+    u->final_w = b.vec("final_conv.1.weight", kDof * d[1]);
+    u->final_b = b.vec("final_conv.1.bias", kDof);
+  }
 
   // time-embedding table: TimeEmbedding (blocks.py:76-92) then each block's TimeMLP (:58-72)
   u->temb_width = b.temb_width;
@@ -794,7 +1060,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
     unet_destroy(u);
     return 1;
   }
-  u->n_launches = (int)u->layers.size() + 1;
+  u->n_launches = (int)u->layers.size() + (u->final_fused ? 0 : 1);
   *out = u;
   return 0;
 }
@@ -808,9 +1074,22 @@ void unet_destroy(UNet* u) {
 int unet_precision(const UNet* u) { return u->precision; }
 int unet_launches(const UNet* u) { return u->n_launches; }
 
-static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row, int rows, cudaStream_t st) {
+static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row, int rows, float* eps, cudaStream_t st) {
   const float* input_act = u->acts.at("input").p;
-  if (ly.kind == LAYER_SIMT) {
+  if (ly.kind == LAYER_PM) {
+    PmArgs a = ly.pargs;
+    a.rows = rows;
+    a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
+    if (ly.pm_final) a.eps = eps;
+    dim3 grid((rows + kPmRows - 1) / kPmRows);
+    auto k = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm_kernel<TC_EL_F16, 32> : conv_pm_kernel<TC_EL_F16, 64>)
+                                   : (a.cout == 32 ? conv_pm_kernel<TC_EL_BF16, 32> : conv_pm_kernel<TC_EL_BF16, 64>);
+    launch_pdl(k, grid, dim3(kPmThreads), ly.tc_smem, st, a);
+  } else if (ly.kind == LAYER_PM_PACK) {
+    const int total = rows * ly.pack_src.L;
+    auto k = u->tc_el == TC_EL_F16 ? pm_pack_input_kernel<TC_EL_F16> : pm_pack_input_kernel<TC_EL_BF16>;
+    launch_pdl(k, dim3((total + 255) / 256), dim3(256), 0, st, x, rows, ly.pack_src.L, ly.pack_dst.phi, ly.pack_dst.plo);
+  } else if (ly.kind == LAYER_SIMT) {
     ConvArgs a = ly.args;
     a.rows = rows;
     if (a.xa == input_act) a.xa = x;   // the first block reads (and its residual re-reads) the caller's x
@@ -840,12 +1119,14 @@ int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStrea
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
-  for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, st);
-  const int threads = 128;
-  const size_t n = (size_t)rows * kHorizon;
-  launch_pdl(final_pw_kernel, dim3((unsigned)((n + threads - 1) / threads)), dim3(threads),
-             (7 * u->final_c + 7) * sizeof(float), st, (const float*)u->final_in.p, (const float*)u->final_w,
-             (const float*)u->final_b, u->final_c, rows, eps);
+  for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, eps, st);
+  if (!u->final_fused) {
+    const int threads = 128;
+    const size_t n = (size_t)rows * kHorizon;
+    launch_pdl(final_pw_kernel, dim3((unsigned)((n + threads - 1) / threads)), dim3(threads),
+               (7 * u->final_c + 7) * sizeof(float), st, (const float*)u->final_in.p, (const float*)u->final_w,
+               (const float*)u->final_b, u->final_c, rows, eps);
+  }
   EDMP_CK(cudaGetLastError());
   return 0;
 }
@@ -856,21 +1137,24 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
                  cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(iters > 0, "iters must be positive");
-  const int n = (int)u->layers.size() + 1;
+  const int nl = (int)u->layers.size();
+  const int n = nl + (u->final_fused ? 0 : 1);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) EDMP_CK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
   for (int it = 0; it < iters; ++it) {
     EDMP_CK(cudaEventRecord(ev[0], st));
-    for (int i = 0; i < n - 1; ++i) {
-      run_layer(u, u->layers[i], x, temb_row, rows, st);
+    for (int i = 0; i < nl; ++i) {
+      run_layer(u, u->layers[i], x, temb_row, rows, eps, st);
       EDMP_CK(cudaEventRecord(ev[i + 1], st));
     }
-    const size_t ne = (size_t)rows * kHorizon;
-    final_pw_kernel<<<(unsigned)((ne + 127) / 128), 128, (7 * u->final_c + 7) * sizeof(float), st>>>(
-        u->final_in.p, u->final_w, u->final_b, u->final_c, rows, eps);
-    EDMP_CK(cudaEventRecord(ev[n], st));
+    if (!u->final_fused) {
+      const size_t ne = (size_t)rows * kHorizon;
+      final_pw_kernel<<<(unsigned)((ne + 127) / 128), 128, (7 * u->final_c + 7) * sizeof(float), st>>>(
+          u->final_in.p, u->final_w, u->final_b, u->final_c, rows, eps);
+      EDMP_CK(cudaEventRecord(ev[n], st));
+    }
     EDMP_CK(cudaStreamSynchronize(st));
     for (int i = 0; i < n; ++i) {
       float m = 0.f;
@@ -880,7 +1164,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
   }
   for (int i = 0; i < n; ++i) {
     ms[i] = (float)(acc[i] / iters);
-    macs[i] = i < n - 1 ? u->layers[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
+    macs[i] = i < nl ? u->layers[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return 0;
@@ -897,7 +1181,7 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
   EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 8 * sizeof(long long), st));
   u->dbg = d;
   const float* temb_row = u->temb;
-  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, st);
+  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, nullptr, st);
   u->dbg = nullptr;
   EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   EDMP_CK(cudaStreamSynchronize(st));
@@ -922,6 +1206,10 @@ int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C
     const size_t n = (size_t)rows * a.C * a.L;
     if (a.p) {
       EDMP_CK(cudaMemcpyAsync(out, a.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (a.phi) {
+      auto unpack = u->tc_el == TC_EL_F16 ? pm_unpack_kernel<TC_EL_F16> : pm_unpack_kernel<TC_EL_BF16>;
+      unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.phi, a.plo, rows, a.C, a.L, out);
+      EDMP_CK(cudaGetLastError());
     } else {
       auto unpack = u->tc_el == TC_EL_F16 ? tc_unpack_kernel<TC_EL_F16>
                     : u->tc_el == TC_EL_BF16 ? tc_unpack_kernel<TC_EL_BF16> : tc_unpack_kernel<TC_EL_TF32>;
