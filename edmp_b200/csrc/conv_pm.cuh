@@ -78,6 +78,7 @@ struct PmArgs {
   const float *fw, *fb;             // fused final 1x1 conv [7][cout], [7]
   float* eps;                       // [rows][7][lout]
   int rows;
+  long long* dbg;                   // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
 };
 
 __device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, int rby) {
@@ -92,22 +93,37 @@ __device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, i
 
 __device__ __forceinline__ void pm_epi_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kPmEpiThreads) : "memory"); }
 
-template <int EL, int COUT>
-__global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_constant__ PmArgs a) {
+constexpr int kPmCt = 32;   // output channels per CTA (grid.y = cout / 32)
+
+__device__ __forceinline__ void pm_ld_par16(const float* p, float (&o)[16]) {   // 16 floats, 16-byte aligned shared memory
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+    o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+  }
+}
+
+// CG = channels per GroupNorm group of the layer (cout / 8: 4 or 8); a CTA owns kPmCt = 32 output channels
+// = 32 / CG whole groups of 8 trajectory rows.
+template <int EL, int CG>
+__global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_constant__ PmArgs a) {
   static_assert(EL != TC_EL_TF32, "position-major kernels use 16-bit operand elements");
+  constexpr int COUT = kPmCt;
   constexpr int UNITS = COUT / 16;            // 16-column accumulator units per M tile
-  constexpr int CG = COUT / 8;                // channels per GroupNorm group (4 or 8)
+  constexpr int NG = COUT / CG;               // GroupNorm groups in this CTA's channels (8 or 4)
   constexpr int GPU_ = 16 / CG;               // groups per unit (4 or 2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_full, bar_acc;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_par[5 * 64];             // bias | gamma | beta | temb | aux bias
-  __shared__ float s_fw[7 * 64 + 8];          // final 1x1 conv weights + bias
-  __shared__ float s_red[2][kPmEpiWarps][8][8];   // [pass][warp][row][group]
+  __shared__ __align__(16) float s_par[5 * 32];   // bias | gamma | beta | temb | aux bias of this CTA's channels
+  __shared__ float s_fw[7 * 32 + 8];              // final 1x1 conv weights + bias
+  __shared__ float s_red[kPmEpiWarps][8][8];      // [warp][row][group] partial sums
+  __shared__ float s_mr[2][8][8];                 // [mean | rstd][row][group]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x;
+  const int c0 = blockIdx.y * COUT;           // first output channel of this CTA
   const int C = a.a.C;
   const int rby = 2 * C;                      // bytes per (position, row) line
   const int atom = 8 * rby;
@@ -115,8 +131,10 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
   const int nparts = a.split ? 2 : 1;
   const int ntiles = (a.n_m + 15) >> 4;
   uint8_t* a_smem = smem;                                   // [part][source] images
-  uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][cout][rby]
+  uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][32 rows][rby]
 
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     umma::mbar_init(&bar_full, 1);
@@ -132,11 +150,11 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
     if (e < COUT) {
-      s_par[e] = a.bias ? a.bias[e] : 0.0f;
-      s_par[64 + e] = a.gamma ? a.gamma[e] : 1.0f;
-      s_par[128 + e] = a.beta ? a.beta[e] : 0.0f;
-      s_par[192 + e] = a.temb ? a.temb[e] : 0.0f;
-      s_par[256 + e] = a.aux_bias ? a.aux_bias[e] : 0.0f;
+      s_par[e] = a.bias ? a.bias[c0 + e] : 0.0f;
+      s_par[32 + e] = a.gamma ? a.gamma[c0 + e] : 1.0f;
+      s_par[64 + e] = a.beta ? a.beta[c0 + e] : 0.0f;
+      s_par[96 + e] = a.temb ? a.temb[c0 + e] : 0.0f;
+      s_par[128 + e] = a.aux_bias ? a.aux_bias[c0 + e] : 0.0f;
     }
     if (a.eps) {
       for (int i = e; i < 7 * COUT + 7; i += kPmEpiThreads) s_fw[i] = i < 7 * COUT ? a.fw[i] : a.fb[i - 7 * COUT];
@@ -147,6 +165,7 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== producer: the layer's whole operand set in a few bulk copies =====
@@ -159,18 +178,20 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
           const uint8_t* g = (const uint8_t*)(p ? src.lo : src.hi) + (size_t)rb * a.a_bytes_img;
           umma::bulk_g2s(a_smem + (size_t)(p * nkc + s) * a.a_bytes_img, g, (uint32_t)a.a_bytes_img, &bar_full);
         }
-        umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, p ? a.w_lo : a.w_hi, (uint32_t)a.w_bytes_part, &bar_full);
+        umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part,
+                       (const uint8_t*)(p ? a.w_lo : a.w_hi) + (size_t)blockIdx.y * a.w_bytes_part,
+                       (uint32_t)a.w_bytes_part, &bar_full);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
     umma::mbar_wait(&bar_full, 0);
     umma::tc_fence_after();
+    if (dbg && lane == 0) dbg[2] = clock64();
     const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
     const uint32_t a_lo_off = (uint32_t)(nkc * a.a_bytes_img), w_lo_off = (uint32_t)a.w_bytes_part;
     const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
     const int ksteps = C >> 4;
-    const int n_acc = a.n_groups + a.aux;
     for (int mt = 0; mt < ntiles; ++mt) {
       uint32_t touched = 0;
       for (int ti = 0; ti < a.n_terms; ++ti) {
@@ -199,12 +220,13 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
         }
       }
     }
-    (void)n_acc;
     if (umma::elect_one()) umma::mma_commit(&bar_acc);
     __syncwarp();
+    if (dbg && lane == 0) dbg[3] = clock64();
   } else {
     // ===== epilogue =====
     const int ew = warp - 2;
+    const int et = threadIdx.x - 64;
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access (warp id mod 4)
     const int half = ew >> 2;                   // which M tiles (mt & 1 == half)
     const int row = lane & 7;
@@ -214,149 +236,149 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
     umma::mbar_wait(&bar_acc, 0);
     __syncwarp();
     umma::tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
 
-    float mean[8], rstd[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) { mean[g] = 0.0f; rstd[g] = 1.0f; }
     if (a.mode != PM_BIAS) {
       // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26), two-pass
       const float inv_n = 1.0f / (float)(CG * a.n_m);
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
-        float s[8];
+        float s[NG];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) s[g] = 0.0f;
+        for (int g = 0; g < NG; ++g) s[g] = 0.0f;
         for (int mt = half; mt < ntiles; mt += 2) {
           const bool valid = (16 * mt + pos_in_tile) < a.n_m;
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
-            float v[16];
+            float v[16], b[16];
             umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT + u * 16), v);
+            pm_ld_par16(s_par + u * 16, b);
             if (valid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int g = u * GPU_ + i / CG;
-                const float y = fmaf(v[i], a.acc_scale, s_par[u * 16 + i]);
+                const float y = fmaf(v[i], a.acc_scale, b[i]);
                 if (pass == 0) s[g] += y;
-                else { const float d = y - mean[g]; s[g] = fmaf(d, d, s[g]); }
+                else { const float d = y - s_mr[0][row][g]; s[g] = fmaf(d, d, s[g]); }
               }
             }
           }
         }
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < NG; ++g) {
           s[g] += __shfl_xor_sync(0xffffffffu, s[g], 8);
           s[g] += __shfl_xor_sync(0xffffffffu, s[g], 16);
         }
         if (lane < 8) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) s_red[pass][ew][row][g] = s[g];
+          for (int g = 0; g < NG; ++g) s_red[ew][row][g] = s[g];
         }
         pm_epi_barrier();
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        if (et < 8 * NG) {
+          const int r = et / NG, g = et % NG;
           float t = 0.0f;
 #pragma unroll
-          for (int w = 0; w < kPmEpiWarps; ++w) t += s_red[pass][w][row][g];
-          if (pass == 0) mean[g] = t * inv_n;
-          else rstd[g] = rsqrtf(t * inv_n + 1e-5f);
+          for (int w = 0; w < kPmEpiWarps; ++w) t += s_red[w][r][g];
+          s_mr[pass][r][g] = pass == 0 ? t * inv_n : rsqrtf(t * inv_n + 1e-5f);
         }
+        pm_epi_barrier();
       }
     }
 
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const int n_acc = a.n_groups + a.aux;
-    const int rby_o = 2 * COUT;
+    const int rby_o = 2 * a.cout;               // output line bytes (full channel count of the layer)
+    const int chunk0 = c0 >> 3;                 // first 16-byte chunk of this CTA's channels in a line
     for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
       const bool is_aux = a.aux && g_acc == a.n_groups;
+      const bool gn = !is_aux && a.mode != PM_BIAS;
       const float sc = is_aux ? a.aux_scale : a.acc_scale;
-      const float* pb = is_aux ? s_par + 256 : s_par;
+      const float* pb = is_aux ? s_par + 128 : s_par;
       void* o_hi = is_aux ? a.aux_hi : a.out_hi;
       void* o_lo = is_aux ? a.aux_lo : a.out_lo;
       for (int mt = half; mt < ntiles; mt += 2) {
         const int idx = 16 * mt + pos_in_tile;
         const bool valid = idx < a.n_m && grow < a.rows;
         const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
-        float y[COUT];
+        const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
+        float fin[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) fin[j] = 0.0f;
 #pragma unroll
         for (int u = 0; u < UNITS; ++u) {
           float v[16];
           umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT + u * 16), v);
+          {
+            float b[16];
+            pm_ld_par16(pb + u * 16, b);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = fmaf(v[i], sc, pb[u * 16 + i]);
-            if (!is_aux && a.mode != PM_BIAS) {
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc, b[i]);
+          }
+          if (gn) {
+            float ga[16], be[16], te[16];
+            pm_ld_par16(s_par + 32 + u * 16, ga);
+            pm_ld_par16(s_par + 64 + u * 16, be);
+            pm_ld_par16(s_par + 96 + u * 16, te);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
               const int g = u * GPU_ + i / CG;
-              t = (t - mean[g]) * rstd[g] * s_par[64 + u * 16 + i] + s_par[128 + u * 16 + i];
-              t = mish_fast(t) + s_par[192 + u * 16 + i];
+              const float t = (v[i] - s_mr[0][row][g]) * s_mr[1][row][g] * ga[i] + be[i];
+              v[i] = mish_fast(t) + te[i];
             }
-            y[u * 16 + i] = t;
           }
-        }
-        if (!valid) continue;
-        const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
-        if (!is_aux && a.mode == PM_GN_RES) {
-          // out + x (blocks.py:164, identity residual): x = hi + lo of the block input, same layout
-#pragma unroll
-          for (int c = 0; c < COUT / 8; ++c) {
-            const size_t off = line + (size_t)(pm_swz(rby_o, row, c) << 4);
-            const uint4 h = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
-            uint4 l = make_uint4(0, 0, 0, 0);
-            if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
-            float x[8];
-            tc_chunk_sum<EL>(h, l, a.res.lo != nullptr, x);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y[c * 8 + e] += x[e];
-          }
-        }
-        if (o_hi) {
-#pragma unroll
-          for (int u = 0; u < UNITS; ++u) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = y[u * 16 + i];
-            uint4 h[4], l[4];
-            tc_split_store<EL>(v, o_lo != nullptr, h, l);
+          if (!valid) continue;
+          if (!is_aux && a.mode == PM_GN_RES) {
+            // out + x (blocks.py:164, identity residual): x = hi + lo of the block input, same layout
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-              const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
-              *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
-              if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
+              const size_t off = line + (size_t)(pm_swz(rby_o, row, chunk0 + 2 * u + m) << 4);
+              const uint4 h = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+              uint4 l = make_uint4(0, 0, 0, 0);
+              if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
+              float x[8];
+              tc_chunk_sum<EL>(h, l, a.res.lo != nullptr, x);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[m * 8 + e] += x[e];
             }
           }
-        }
-        if (!is_aux && a.tc_hi) {
-          // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
-          const int rt = grow / kTcRows, rl = grow % kTcRows;
-          const int kch = COUT / 64;
-#pragma unroll
-          for (int u = 0; u < UNITS; ++u) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = y[u * 16 + i];
+          if (o_hi || (!is_aux && a.tc_hi)) {
             uint4 h[4], l[4];
-            tc_split_store<EL>(v, a.tc_lo != nullptr, h, l);
-            const int k = lo * COUT + u * 16;
-            const size_t blk = ((size_t)rt * (a.lout * kch) + (k >> 6)) * kTcBlockBytes;
+            tc_split_store<EL>(v, (is_aux ? a.aux_lo : (a.tc_hi ? a.tc_lo : a.out_lo)) != nullptr, h, l);
+            if (o_hi) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const size_t off = blk + tc_swz_bytes(rl, ((k & 63) >> 3) + m);
-              *reinterpret_cast<uint4*>((uint8_t*)a.tc_hi + off) = h[m];
-              if (a.tc_lo) *reinterpret_cast<uint4*>((uint8_t*)a.tc_lo + off) = l[m];
+              for (int m = 0; m < 2; ++m) {
+                const size_t off = line + (size_t)(pm_swz(rby_o, row, chunk0 + 2 * u + m) << 4);
+                *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
+                if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
+              }
+            } else {
+              // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
+              const int rt = grow / kTcRows, rl = grow % kTcRows;
+              const int k = lo * a.cout + c0 + u * 16;
+              const size_t blk = ((size_t)rt * (a.lout * (a.cout >> 6)) + (k >> 6)) * kTcBlockBytes;
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                const size_t off = blk + tc_swz_bytes(rl, ((k & 63) >> 3) + m);
+                *reinterpret_cast<uint4*>((uint8_t*)a.tc_hi + off) = h[m];
+                if (a.tc_lo) *reinterpret_cast<uint4*>((uint8_t*)a.tc_lo + off) = l[m];
+              }
             }
           }
-        }
-        if (!is_aux && a.eps) {
-          // fused final nn.Conv1d(C, 7, 1) (temporalunet.py:36)
+          if (!is_aux && a.eps) {
+            // fused final nn.Conv1d(32, 7, 1) (temporalunet.py:36): partial sums over this unit's channels
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            float acc = s_fw[7 * COUT + j];
+            for (int j = 0; j < 7; ++j)
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc = fmaf(s_fw[j * COUT + c], y[c], acc);
-            a.eps[((size_t)grow * 7 + j) * a.lout + lo] = acc;
+              for (int i = 0; i < 16; ++i) fin[j] = fmaf(s_fw[j * COUT + u * 16 + i], v[i], fin[j]);
           }
+        }
+        if (valid && !is_aux && a.eps) {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) a.eps[((size_t)grow * 7 + j) * a.lout + lo] = fin[j] + s_fw[7 * COUT + j];
         }
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     umma::tc_fence_before();
   }
   __syncthreads();
@@ -364,6 +386,7 @@ __global__ void __launch_bounds__(kPmThreads) conv_pm_kernel(const __grid_consta
     umma::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
   }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 // x float32 [rows][7][50]  ->  position-major image with C = 16 (channels 7..15 zero), hi / lo halves.

@@ -685,11 +685,12 @@ struct Builder {
     }
   }
 
-  // weights of one slot group into [slot][k chunk][cout rows][2C bytes] swizzled images (hi, lo);
-  // wfn(co, ci, slot).  Returns the exact inverse of the power-of-two scale.
+  // weights of one slot group into [32-channel column tile][slot][k chunk][32 rows][2C bytes] swizzled
+  // images (hi, lo); total_slots = slots per column tile; wfn(co, ci, slot).  Returns the exact inverse of
+  // the power-of-two scale.
   template <class F>
-  float pack_pm_slots(std::vector<uint8_t>& hi, std::vector<uint8_t>& lo, int slot0, int n_slots, int cout, int C,
-                      int nkc, F wfn) {
+  float pack_pm_slots(std::vector<uint8_t>& hi, std::vector<uint8_t>& lo, int slot0, int n_slots, int total_slots,
+                      int cout, int C, int nkc, F wfn) {
     const int rby = 2 * C;
     float scale = 1.0f;
     if (u->tc_el == TC_EL_F16) {
@@ -709,7 +710,9 @@ struct Builder {
             const float w = scale * wfn(co, kc * C + c, sl);
             const int r8 = co & 7, chunk = (c * 2) >> 4;
             const int sw = rby == 128 ? (chunk ^ r8) : (rby == 64 ? (chunk ^ ((r8 >> 1) & 3)) : (chunk ^ ((r8 >> 2) & 1)));
-            const size_t off = ((size_t)((slot0 + sl) * nkc + kc) * cout + co) * rby + (size_t)(sw << 4) + ((c * 2) & 15);
+            const int nh = co / kPmCt, cl = co % kPmCt;
+            const size_t off = ((size_t)((nh * total_slots + slot0 + sl) * nkc + kc) * kPmCt + cl) * rby + (size_t)(sw << 4) +
+                               ((c * 2) & 15);
             uint16_t h, l;
             encode16(w, &h, &l);
             std::memcpy(&hi[off], &h, 2);
@@ -726,18 +729,18 @@ struct Builder {
     t.a_bytes_img = (t.lin + 4) * atom;
     const int nimg = nkc * nparts;
     t.a_bytes_total = nimg * t.a_bytes_img;
-    t.w_bytes_part = n_slots * nkc * t.cout * rby;
+    t.w_bytes_part = n_slots * nkc * kPmCt * rby;   // per 32-channel column tile
     // the last M tile reads (finite garbage) past the last image: that tail may overlap the weights
     const size_t tail_end = (size_t)(nimg - 1) * t.a_bytes_img + (size_t)atoms_needed * atom;
     const int ntiles = (t.n_m + 15) / 16;
-    int cols = (t.n_groups + t.aux) * ntiles * t.cout, p2 = 32;
+    int cols = (t.n_groups + t.aux) * ntiles * kPmCt, p2 = 32;
     while (p2 < cols) p2 *= 2;
     t.tmem_cols = p2;
     ok = ok && p2 <= 512;
     ly.kind = LAYER_PM;
     ly.tc_smem = 1024 + std::max((((size_t)t.a_bytes_total + 1023) & ~(size_t)1023) + (size_t)nparts * t.w_bytes_part,
                                  tail_end) + 256;
-    ok = ok && ly.tc_smem <= 232448 - 9216 - 1024;
+    ok = ok && ly.tc_smem <= 232448 - 6144 - 1024;
   }
 
   // Conv1dBlock (conv5 + GroupNorm + Mish [+ time embedding] [+ identity residual]) on the
@@ -768,7 +771,7 @@ struct Builder {
     std::vector<uint8_t> hi((size_t)n_slots * nkc * cout * rby), lo(hi.size());
     const float* w = P(p + ".block.0.weight");   // [cout][cin_real][5]; the packed input has C >= cin_real channels
     const int cin_real = pw->table.at(p + ".block.0.weight").d1;
-    t.acc_scale = pack_pm_slots(hi, lo, 0, 5, cout, C, nkc, [&](int co, int ci, int sl) {
+    t.acc_scale = pack_pm_slots(hi, lo, 0, 5, n_slots, cout, C, nkc, [&](int co, int ci, int sl) {
       return ci < cin_real ? w[((size_t)co * cin_real + ci) * 5 + sl] : 0.0f;
     });
     if (aux) {
@@ -776,7 +779,7 @@ struct Builder {
       t.aux = 1;
       t.terms[5].acc = 1; t.terms[5].slot = 5; t.terms[5].off = 2;
       t.n_terms = 6;
-      t.aux_scale = pack_pm_slots(hi, lo, 5, 1, cout, C, nkc, [&](int co, int ci, int) {
+      t.aux_scale = pack_pm_slots(hi, lo, 5, 1, n_slots, cout, C, nkc, [&](int co, int ci, int) {
         return ci < cin_real ? wr[(size_t)co * cin_real + ci] : 0.0f;
       });
       t.aux_bias = vec(aux_prefix + ".residual_conv.bias", cout);
@@ -855,7 +858,7 @@ struct Builder {
       atoms_needed = 16 * ((L + 15) / 16) + 4;
     }
     std::vector<uint8_t> hi((size_t)n_slots * C * rby), lo(hi.size());
-    t.acc_scale = pack_pm_slots(hi, lo, 0, n_slots, C, C, 1, [&](int co, int ci, int sl) {
+    t.acc_scale = pack_pm_slots(hi, lo, 0, n_slots, n_slots, C, C, 1, [&](int co, int ci, int sl) {
       return up ? w[((size_t)ci * C + co) * 4 + sl] : w[((size_t)co * C + ci) * 3 + sl];
     });
     t.w_hi = upload_bytes(u, hi.data(), hi.size());
@@ -950,10 +953,10 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9216 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       attr_set = true;
     }
   }
@@ -1081,9 +1084,10 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.rows = rows;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     if (ly.pm_final) a.eps = eps;
-    dim3 grid((rows + kPmRows - 1) / kPmRows);
-    auto k = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm_kernel<TC_EL_F16, 32> : conv_pm_kernel<TC_EL_F16, 64>)
-                                   : (a.cout == 32 ? conv_pm_kernel<TC_EL_BF16, 32> : conv_pm_kernel<TC_EL_BF16, 64>);
+    a.dbg = u->dbg;
+    dim3 grid((rows + kPmRows - 1) / kPmRows, a.cout / kPmCt);
+    auto k = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm_kernel<TC_EL_F16, 4> : conv_pm_kernel<TC_EL_F16, 8>)
+                                   : (a.cout == 32 ? conv_pm_kernel<TC_EL_BF16, 4> : conv_pm_kernel<TC_EL_BF16, 8>);
     launch_pdl(k, grid, dim3(kPmThreads), ly.tc_smem, st, a);
   } else if (ly.kind == LAYER_PM_PACK) {
     const int total = rows * ly.pack_src.L;
@@ -1172,20 +1176,25 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
 
 // debug: run op `op` alone `iters` times and return the clock64 stamps of its CTAs ([ctas][8])
 int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st) {
-  EDMP_REQUIRE(op >= 0 && op < (int)u->layers.size() && u->layers[op].kind == LAYER_TC, "op is not a tensor-core layer");
+  EDMP_REQUIRE(op >= 0 && op < (int)u->layers.size() &&
+                   (u->layers[op].kind == LAYER_TC || u->layers[op].kind == LAYER_PM), "op is not a tensor-core layer");
   Layer& ly = u->layers[op];
-  const int ctas = ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
+  const int ctas = ly.kind == LAYER_PM ? ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt)
+                                       : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;
   EDMP_CK(cudaMalloc(&d, (size_t)ctas * 8 * sizeof(long long)));
   EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 8 * sizeof(long long), st));
   u->dbg = d;
   const float* temb_row = u->temb;
-  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, nullptr, st);
+  float* eps_tmp = nullptr;
+  if (ly.pm_final) EDMP_CK(cudaMalloc(&eps_tmp, (size_t)rows * kRowElems * sizeof(float)));
+  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, eps_tmp, st);
   u->dbg = nullptr;
   EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   EDMP_CK(cudaStreamSynchronize(st));
   cudaFree(d);
+  if (eps_tmp) cudaFree(eps_tmp);
   *n_ctas = ctas;
   return 0;
 }

@@ -23,15 +23,16 @@ torch.cuda.synchronize()
 lib = _lib.load()
 h = m.engine(rows)
 n_ops = lib.edmp_unet_launches_per_forward(h)
-buf = np.zeros((4096, 8), dtype=np.int64)
+buf = np.zeros((8192, 8), dtype=np.int64)
 labels = ["setup", "wait W0", "wait A0", "mainloop issue", "acc ready", "epilogue", "teardown"]
 for i in range(n_ops - 1):
     n = ctypes.c_int()
-    rc = lib.edmp_unet_tc_trace(h, i, rows, buf.ctypes.data_as(ctypes.c_void_p), 4096, ctypes.byref(n), None)
+    rc = lib.edmp_unet_tc_trace(h, i, rows, buf.ctypes.data_as(ctypes.c_void_p), 8192, ctypes.byref(n), None)
     if rc != 0:
         continue
     t = buf[:n.value].astype(np.float64)
     d = np.diff(t, axis=1)
     total = t[:, 7] - t[:, 0]
-    print("%-36s ctas %3d  total %7.0f cyc (%5.1f us @1.9GHz) | " % (lib.edmp_unet_op_name(h, i).decode(), n.value,
-          total.mean(), total.mean() / 1900.0) + "  ".join("%s %6.0f" % (l, v) for l, v in zip(labels, d.mean(axis=0))))
+    span = (t[:, 7].max() - t[:, 0].min())
+    print("%-36s ctas %4d  span %8.0f  total %7.0f cyc (%5.1f us @1.9GHz) | " % (lib.edmp_unet_op_name(h, i).decode(), n.value,
+          span, total.mean(), total.mean() / 1900.0) + "  ".join("%s %6.0f" % (l, v) for l, v in zip(labels, d.mean(axis=0))))
