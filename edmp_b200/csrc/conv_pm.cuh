@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
   uint8_t* a_smem = smem;                                   // [part][source] images
   uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][32 rows][rby]
 
-  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
   if (threadIdx.x == 0) {

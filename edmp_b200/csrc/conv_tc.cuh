@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, nt = blockIdx.y;
-  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
 
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // cost of one M=128 SS-mode MMA is ~40 + N/2 cycles for tf32 (K=8) and bf16 (K=16) alike
     // (tools/micro/mma_rate.cu), so bf16 operands halve the mainloop. =====
     int a_it = 0, b_it = 0;
+    long long wait_a = 0, wait_b = 0;
     const uint64_t desc0 = umma::make_desc_sw128(0);
     for (int p = 0; p < a.n_phases; ++p) {
       const TcPhase& ph = a.ph[p];
@@ -311,14 +312,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       uint32_t touched = 0;   // output positions whose accumulator columns already hold a partial sum
       for (int cc = 0; cc < kc_total; ++cc) {
         const int bs = b_it % a.b_stages;
-        umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1);
+        { const long long tw = dbg ? clock64() : 0; umma::mbar_wait(b_full + bs, (b_it / a.b_stages) & 1); if (dbg) wait_b += clock64() - tw; }
         if (dbg && b_it == 0 && lane == 0) dbg[2] = clock64();
         const uint32_t b_base = umma::smem_u32(b_smem + bs * b_stage_bytes);
         for (int li = 0; li < ph.lin; ++li) {
           const TcSched s = ph.sched[li];
           if (s.n_slots == 0) continue;
           const int as = a_it % a.a_stages;
-          umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1);
+          { const long long tw = dbg ? clock64() : 0; umma::mbar_wait(a_full + as, (a_it / a.a_stages) & 1); if (dbg) wait_a += clock64() - tw; }
           umma::tc_fence_after();
           if (dbg && a_it == 0 && lane == 0) dbg[3] = clock64();
           const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     if (umma::elect_one()) umma::mma_commit(acc_full);
     __syncwarp();
-    if (dbg && lane == 0) dbg[4] = clock64();
+    if (dbg && lane == 0) { dbg[4] = clock64(); dbg[8] = wait_a; dbg[9] = wait_b; dbg[10] = a_it; dbg[11] = b_it; }
   } else {
     // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th
     // 16-column unit of it (four warps share each 32-lane TMEM quarter) =====

@@ -1183,15 +1183,15 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
                                        : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;
-  EDMP_CK(cudaMalloc(&d, (size_t)ctas * 8 * sizeof(long long)));
-  EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 8 * sizeof(long long), st));
+  EDMP_CK(cudaMalloc(&d, (size_t)ctas * 16 * sizeof(long long)));
+  EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 16 * sizeof(long long), st));
   u->dbg = d;
   const float* temb_row = u->temb;
   float* eps_tmp = nullptr;
   if (ly.pm_final) EDMP_CK(cudaMalloc(&eps_tmp, (size_t)rows * kRowElems * sizeof(float)));
   for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, eps_tmp, st);
   u->dbg = nullptr;
-  EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   EDMP_CK(cudaStreamSynchronize(st));
   cudaFree(d);
   if (eps_tmp) cudaFree(eps_tmp);

@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 lib = _lib.load()
 h = m.engine(rows)
 n_ops = lib.edmp_unet_launches_per_forward(h)
-buf = np.zeros((8192, 8), dtype=np.int64)
+buf = np.zeros((8192, 16), dtype=np.int64)
 labels = ["setup", "wait W0", "wait A0", "mainloop issue", "acc ready", "epilogue", "teardown"]
 for i in range(n_ops - 1):
     n = ctypes.c_int()
@@ -31,8 +31,10 @@ for i in range(n_ops - 1):
     if rc != 0:
         continue
     t = buf[:n.value].astype(np.float64)
+    extra = t[:, 8:12].mean(axis=0)
+    t = t[:, :8]
     d = np.diff(t, axis=1)
     total = t[:, 7] - t[:, 0]
     span = (t[:, 7].max() - t[:, 0].min())
     print("%-36s ctas %4d  span %8.0f  total %7.0f cyc (%5.1f us @1.9GHz) | " % (lib.edmp_unet_op_name(h, i).decode(), n.value,
-          span, total.mean(), total.mean() / 1900.0) + "  ".join("%s %6.0f" % (l, v) for l, v in zip(labels, d.mean(axis=0))))
+          span, total.mean(), total.mean() / 1900.0) + "  ".join("%s %6.0f" % (l, v) for l, v in zip(labels, d.mean(axis=0))) + "  | waitA %6.0f waitB %6.0f a_it %3.0f b_it %3.0f" % tuple(extra))
