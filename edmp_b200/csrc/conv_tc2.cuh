@@ -1,0 +1,602 @@
+// Persistent tensor-core (tcgen05 + TMEM) convolution kernel for the TemporalUNet levels with horizon <= 13,
+// second generation of conv_tc.cuh (same GEMM view, same operand layouts in HBM, 16-bit operand elements):
+//
+//   D[row, (l_out, c_out)] = sum_{(l_in, c_in)} X[row, (l_in, c_in)] * W      ("rows as M", windowed implicit GEMM)
+//
+// What changed, and the measurement behind each change (profiles/micro/r1_*.txt, tools/micro/*.cu):
+//   * tcgen05.mma issue is effectively synchronous with execution (queue depth ~1, >= 40 cycles per M=128
+//     instruction): every cycle the issuing thread spends on waits / index arithmetic between MMAs is a cycle the
+//     tensor pipe idles.  The issue loop is therefore lean (stage counters instead of div/mod, commit inside the
+//     elected region, at most two MMA runs per step for the first K chunk) and the first-chunk accumulate flags
+//     are precomputed on the host.
+//   * one CTA per SM stays resident and walks tiles (row tile, column tile) of the layer: no per-tile TMEM
+//     allocation / barrier setup, no wave quantisation, and -- with two TMEM accumulator buffers -- the epilogue
+//     of tile i runs under the mainloop of tile i+1.
+//   * the operand producer is one dedicated thread that polls both streams (activations, weights) and runs ahead
+//     across tile boundaries; a bulk copy has ~1.3k cycles of latency, so throughput is set by bytes in flight,
+//     not by the number of issuing threads.
+//   * the epilogue keeps a thread's accumulator values in registers: ONE TMEM read (then the buffer is handed back
+//     to the MMA warp at once), GroupNorm statistics two-pass on registers with per-unit partials meeting in shared
+//     memory among the four warps of a TMEM lane quarter, results stored straight to the tiled layout the next
+//     layer consumes -- no shared-memory staging, which would compete with the MMA operand fetch for the
+//     128 B/cycle of shared-memory bandwidth (the binding resource of SS-mode MMAs at N <= 128).
+//   * CG = 2: cta_group::2 -- a CTA pair (two row tiles, same column tile) shares each weight tile: every CTA
+//     stages only half of it and the pair's MMA (M = 256) reads A from both CTAs, halving the weight traffic
+//     and the shared-memory operand bandwidth per CTA.
+//
+// Reference ops covered: Conv1dBlock (blocks.py:13-34), ResidualConvolutionBlock (:137-166) incl. the 1x1
+// residual conv (second accumulator), stride-2 Conv1d (:211), ConvTranspose1d (:249).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace edmp {
+
+constexpr int kT2EpiWarp0 = 2;                       // warp 0: operand producer, 1: TMEM + MMA issue
+constexpr int kT2EpiWarps = 16;
+constexpr int kT2EpiThreads = kT2EpiWarps * 32;
+constexpr int kT2Threads = (kT2EpiWarp0 + kT2EpiWarps) * 32;   // 576
+constexpr int kT2MaxAStages = 4, kT2MaxBStages = 3;
+constexpr int kT2MaxUnits = 16;                      // accumulator columns per tile <= 256
+
+struct Tc2Sched {       // what one K chunk at input position l_in contributes to
+  int8_t slot_begin;    // first weight slot
+  int8_t n_slots;       // consecutive output positions touched (0: position unused)
+  int8_t lo_begin;      // first output position
+  int8_t n_acc;         // first K chunk only: leading positions of the window that already hold a partial sum
+};
+
+struct Tc2Phase {
+  TcOperand a, b;       // b.C == 0 unless the input is a skip concat (blocks.py:253)
+  const void* w_hi;     // packed weights [n_tile][c_chunk][CG halves][slots * ct / CG rows][128 B] swizzled
+  const void* w_lo;
+  float acc_scale;      // exact inverse of the power-of-two weight scale
+  int lin, slots;
+  int d_col;            // accumulator column base inside a buffer
+  int col_step;         // accumulator columns per output position in the MMA's D address (ct, or ct/2 for the
+                        // [half][position][ct/2] layout of a cta_group::2 full-window phase)
+  Tc2Sched sched[kTcMaxLin];
+};
+
+struct Tc2Args {
+  Tc2Phase ph[2];
+  int n_phases;
+  int rows, lout, ct, cout, cg, mode, split;
+  int a_stages, b_stages;
+  int acc_bufs, acc_stride;       // TMEM accumulator buffers (1 or 2) and their column stride
+  int half_layout;                // 1: phase-0 accumulator columns are [half][position][ct/2] (cta_group::2)
+  int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
+  const float *bias, *gamma, *beta, *temb, *bres;
+  TcOperand res;                  // identity residual source (tiled)
+  void *out_hi, *out_lo;          // tiled output (or position-major images when out_pm)
+  int out_pm;
+  long long* dbg;                 // optional [ctas][16] clock64 stamps / counters, normally null
+};
+
+namespace t2 {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mma_f16_cg2(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void commit_cg2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   umma::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on a barrier of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(umma::smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// wait without the diagnostic printf of umma::mbar_wait in the hot loops (still bounded: traps instead of hanging)
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!umma::mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+// non-blocking phase test
+__device__ __forceinline__ bool test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(umma::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bar_quarter(int quarter) {   // the four epilogue warps sharing a TMEM lane quarter
+  asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
+}
+__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 5, %0;" ::"n"(kT2EpiThreads) : "memory"); }
+}  // namespace t2
+
+template <int EL, int CG>
+__global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args a) {
+  static_assert(EL != TC_EL_TF32, "conv_tc2 uses 16-bit operand elements");
+  using E = TcElem<EL>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_full[kT2MaxAStages], a_empty[kT2MaxAStages], b_full[kT2MaxBStages], b_empty[kT2MaxBStages];
+  __shared__ uint64_t pa_full[kT2MaxAStages], pb_full[kT2MaxBStages];   // CG = 2, leader: "the peer's stage is full"
+  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_par[5 * 128];            // bias | gamma | beta | temb | bres of this column tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? t2::cluster_ctarank() : 0u;
+  const int nparts = a.split ? 2 : 1;
+  const int a_stage_bytes = kTcBlockBytes * nparts;
+  int max_slots = a.ph[0].slots;
+  if (a.n_phases > 1 && a.ph[1].slots > max_slots) max_slots = a.ph[1].slots;
+  const int ctl = a.ct / CG;                                // weight rows per slot staged by this CTA
+  const int b_part_bytes = max_slots * ctl * 128;
+  const int b_stage_bytes = b_part_bytes * nparts;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + a.a_stages * a_stage_bytes;
+  float* s_part = reinterpret_cast<float*>(b_smem + a.b_stages * b_stage_bytes);   // GroupNorm pieces [piece][mean | M2][128 rows]
+  const int n_tiles = (a.n_row_tiles / CG) * a.n_col_tiles;
+  const int unit0 = blockIdx.x / CG, n_walkers = gridDim.x / CG;
+
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  pdl_launch_dependents();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); umma::mbar_init(pa_full + i, 1); }
+    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, 1); umma::mbar_init(pb_full + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, 1); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(&tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      umma::tmem_alloc<512>(&tmem_slot);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (CG == 2) t2::cluster_sync_all();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel; activations are read below
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+
+  if (warp == 0) {
+    // ===== operand producer: ONE thread polls the "stage empty" barriers of both streams (activations, weights)
+    // without blocking and issues bulk copies of ready-made operand blocks; both streams run ahead across tile
+    // boundaries as far as the stages allow =====
+    if (lane == 0) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      int ta = unit0, pa = 0, cca = 0, lia = 0;     // activation stream position (tile, phase, chunk, input position)
+      int tb = unit0, pb = 0, ccb = 0;              // weight stream position
+      // skip leading unused positions
+      while (ta < n_tiles && a.ph[pa].sched[lia].n_slots == 0) ++lia;
+      while (ta < n_tiles || tb < n_tiles) {
+        if (ta < n_tiles && t2::test(a_empty + as, aph ^ 1)) {
+          const Tc2Phase& ph = a.ph[pa];
+          const int ka = ph.a.C >> E::kShift, kb = ph.b.C >> E::kShift;
+          const bool first = cca < ka;
+          const TcOperand& op = first ? ph.a : ph.b;
+          const int c2 = first ? cca : cca - ka;
+          const int kop = first ? ka : kb;
+          const int rt = (ta / a.n_col_tiles) * CG + (int)rank;
+          const size_t blk = ((size_t)rt * (ph.lin * kop) + (size_t)lia * kop + c2) * kTcBlockBytes;
+          umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
+          uint8_t* dst = a_smem + as * a_stage_bytes;
+          umma::bulk_g2s(dst, (const uint8_t*)op.hi + blk, kTcBlockBytes, a_full + as);
+          if (a.split) umma::bulk_g2s(dst + kTcBlockBytes, (const uint8_t*)op.lo + blk, kTcBlockBytes, a_full + as);
+          if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+          // advance (tile, phase, chunk, position), skipping unused positions
+          do {
+            if (++lia == ph.lin) {
+              lia = 0;
+              if (++cca == ka + kb) {
+                cca = 0;
+                if (++pa == a.n_phases) { pa = 0; ta += n_walkers; }
+              }
+            }
+          } while (ta < n_tiles && a.ph[pa].sched[lia].n_slots == 0);
+        }
+        if (tb < n_tiles && t2::test(b_empty + bs, bph ^ 1)) {
+          const Tc2Phase& ph = a.ph[pb];
+          const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+          const int nt = tb % a.n_col_tiles;
+          const uint32_t wtile_bytes = (uint32_t)(ph.slots * ctl * 128);
+          const size_t woff = (((size_t)nt * kc + ccb) * CG + rank) * wtile_bytes;
+          umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes * (uint32_t)nparts);
+          uint8_t* dst = b_smem + bs * b_stage_bytes;
+          umma::bulk_g2s(dst, (const uint8_t*)ph.w_hi + woff, wtile_bytes, b_full + bs);
+          if (a.split) umma::bulk_g2s(dst + b_part_bytes, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
+          if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
+          if (++ccb == kc) {
+            ccb = 0;
+            if (++pb == a.n_phases) { pb = 0; tb += n_walkers; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    if (CG == 2 && rank == 1) {
+      // ===== peer of a CTA pair: relay "my stage is full" to the leader, which issues the MMAs for both =====
+      for (int t = unit0; t < n_tiles; t += n_walkers) {
+        for (int p = 0; p < a.n_phases; ++p) {
+          const Tc2Phase& ph = a.ph[p];
+          const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+          for (int cc = 0; cc < kc; ++cc) {
+            t2::wait(b_full + bs, bph);
+            if (lane == 0) t2::mbar_arrive_remote(pb_full + bs, 0);
+            __syncwarp();
+            for (int li = 0; li < ph.lin; ++li) {
+              if (ph.sched[li].n_slots == 0) continue;
+              t2::wait(a_full + as, aph);
+              if (lane == 0) t2::mbar_arrive_remote(pa_full + as, 0);
+              __syncwarp();
+              if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+            }
+            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    } else {
+      // ===== MMA issuer: warp-uniform walk, one elected lane issues =====
+      const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
+      const uint64_t desc0 = umma::make_desc_sw128(0);
+      uint32_t buf = 0, eph = 0;   // accumulator buffer and the parity of its "empty" barrier
+      long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0;
+      for (int t = unit0; t < n_tiles; t += n_walkers) {
+        {
+          const long long tw = dbg ? clock64() : 0;
+          t2::wait(acc_empty + buf, eph ^ 1);
+          if (dbg) w_acc += clock64() - tw;
+        }
+        umma::tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * (uint32_t)a.acc_stride;
+        for (int p = 0; p < a.n_phases; ++p) {
+          const Tc2Phase& ph = a.ph[p];
+          const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+          for (int cc = 0; cc < kc; ++cc) {
+            {
+              const long long tw = dbg ? clock64() : 0;
+              t2::wait(b_full + bs, bph);
+              if (CG == 2) t2::wait(pb_full + bs, bph);
+              if (dbg) w_b += clock64() - tw;
+            }
+            const uint32_t b_base = b0 + bs * (uint32_t)b_stage_bytes;
+            for (int li = 0; li < ph.lin; ++li) {
+              const Tc2Sched s = ph.sched[li];
+              if (s.n_slots == 0) continue;
+              {
+                const long long tw = dbg ? clock64() : 0;
+                t2::wait(a_full + as, aph);
+                if (CG == 2) t2::wait(pa_full + as, aph);
+                if (dbg) w_a += clock64() - tw;
+              }
+              const uint32_t a_base = a0 + as * (uint32_t)a_stage_bytes;
+              const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+              const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+              // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are
+              // written for the first time -> two runs with their own accumulate flag; afterwards one run
+              const int n_first = (cc == 0) ? s.n_acc : s.n_slots;
+              const bool last_li_of_chunk = false;
+              (void)last_li_of_chunk;
+#pragma unroll 1
+              for (int run = 0; run < 2; ++run) {
+                const int sl0 = run == 0 ? 0 : n_first;
+                const int n = run == 0 ? n_first : s.n_slots - n_first;
+                if (n <= 0) continue;
+                const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows * CG, n * a.ct);
+                const uint32_t d = acc0 + (uint32_t)(ph.d_col + (s.lo_begin + sl0) * ph.col_step);
+                const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + sl0) * ctl * 128);
+                const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
+                const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_part_bytes) & 0x3FFFF) >> 4);
+                const uint32_t accf = run == 0 ? 1u : 0u;
+                if (umma::elect_one()) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
+                    const uint32_t acc = accf | (uint32_t)(ks > 0);
+                    if (CG == 2) {
+                      if (a.split) {
+                        t2::mma_f16_cg2(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                      } else {
+                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                      }
+                    } else {
+                      if (a.split) {
+                        umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                        umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                        umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                      } else {
+                        umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                      }
+                    }
+                  }
+                }
+                __syncwarp();
+              }
+              if (umma::elect_one()) {   // frees the A stage (in both CTAs of a pair) once these MMAs have read it
+                if (CG == 2) t2::commit_cg2(a_empty + as); else umma::mma_commit(a_empty + as);
+              }
+              __syncwarp();
+              if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+            }
+            if (umma::elect_one()) {
+              if (CG == 2) t2::commit_cg2(b_empty + bs); else umma::mma_commit(b_empty + bs);
+            }
+            __syncwarp();
+            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
+          }
+        }
+        if (umma::elect_one()) {
+          if (CG == 2) t2::commit_cg2(acc_full + buf); else umma::mma_commit(acc_full + buf);
+        }
+        __syncwarp();
+        if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) eph ^= 1; } else { eph ^= 1; }
+      }
+      if (dbg && lane == 0) { dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = w_a; dbg[5] = clock64() - t_begin; }
+    }
+  } else {
+    // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th 16-column unit =====
+    const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+    const int part = (warp - kT2EpiWarp0) >> 2;           // which share of the column units (0..3)
+    const int et = threadIdx.x - kT2EpiWarp0 * 32;
+    const int row_local = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int L = a.lout, ct = a.ct, cg = a.cg;
+    const int n_units = (L * ct) >> 4;
+    const bool two = cg == 8;                             // a 16-column unit spans two GroupNorm groups
+    const float inv_n = 1.0f / (float)(cg * L);
+    const float sc0 = a.ph[0].acc_scale, sc1 = a.ph[1].acc_scale;
+    const int kch_out = a.cout >> E::kShift;
+    const int half_cols = (L * ct) >> 1;                  // half_layout: columns of one half
+    float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
+    uint32_t buf = 0, fph = 0;
+    long long w_full = 0, t_busy = 0;
+    bool first_tile = true;
+    for (int t = unit0; t < n_tiles; t += n_walkers) {
+      const int nt = t % a.n_col_tiles;
+      const int rt = (t / a.n_col_tiles) * CG + (int)rank;
+      const int grow = rt * kTcRows + row_local;
+      // ---- per-channel parameters of this column tile ----
+      if (!first_tile) t2::bar_epilogue();                // every reader of the previous tile's parameters is done
+      first_tile = false;
+      for (int e = et; e < 5 * ct; e += kT2EpiThreads) {
+        const int which = e / ct, c = e - which * ct;
+        const float* src = which == 0 ? a.bias : which == 1 ? a.gamma : which == 2 ? a.beta : which == 3 ? a.temb : a.bres;
+        s_par[which * 128 + c] = src ? src[nt * ct + c] : (which == 1 ? 1.0f : 0.0f);
+      }
+      t2::bar_epilogue();
+      {
+        const long long tw = dbg ? clock64() : 0;
+        t2::wait(acc_full + buf, fph);
+        if (dbg) w_full += clock64() - tw;
+      }
+      const long long t_start = dbg ? clock64() : 0;
+      __syncwarp();
+      umma::tc_fence_after();
+      const uint32_t t_acc = t_lane + buf * (uint32_t)a.acc_stride;
+
+      // ---- my units: unit u = part + 4k covers accumulator columns [16u, 16u+16) ----
+      int lo_k[4], c0_k[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = (part + 4 * k) << 4;
+        if (a.half_layout) {
+          const int h = col >= half_cols ? 1 : 0, rem = col - h * half_cols;
+          lo_k[k] = rem / (ct >> 1);
+          c0_k[k] = h * (ct >> 1) + rem % (ct >> 1);
+        } else {
+          lo_k[k] = col / ct;
+          c0_k[k] = col % ct;
+        }
+      }
+      float mean[4][2], rstd[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { mean[k][0] = mean[k][1] = 0.0f; rstd[k][0] = rstd[k][1] = 1.0f; }
+      if (a.mode != TC_BIAS) {
+        // GroupNorm(8) over (cg channels x L positions) of this row (blocks.py:24-26).  Every 16-column unit (8-column
+        // half when groups have 8 channels) yields an exact two-pass (mean, M2) on registers; the pieces of a group
+        // meet in shared memory among the four warps of this lane quarter and are combined with
+        // M2 = sum M2_i + n_i * sum (mean_i - mean)^2 -- no E[x^2] - mean^2 cancellation anywhere.
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = part + 4 * k;
+          if (u < n_units) {
+            float v[16], b[16];
+            umma::tmem_ld16(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), v);
+            pm_ld_par16(s_par + c0_k[k], b);
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = fmaf(v[i], sc0, b[i]);
+              if (i < 8) s0 += v[i]; else s1 += v[i];
+            }
+            const float m0 = two ? s0 * 0.125f : (s0 + s1) * 0.0625f, m1 = two ? s1 * 0.125f : m0;
+            float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float d = v[i] - (i < 8 ? m0 : m1);
+              if (i < 8) q0 = fmaf(d, d, q0); else q1 = fmaf(d, d, q1);
+            }
+            if (two) {
+              my_part[(2 * u) * 256] = m0; my_part[(2 * u) * 256 + 128] = q0;
+              my_part[(2 * u + 1) * 256] = m1; my_part[(2 * u + 1) * 256 + 128] = q1;
+            } else {
+              my_part[u * 256] = m0; my_part[u * 256 + 128] = q0 + q1;
+            }
+          }
+        }
+        t2::bar_quarter(quarter);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = part + 4 * k;
+          if (u < n_units) {
+            if (two) {
+              // groups of 8 channels: the same half of the unit at this channel offset of every position
+              const int cu = c0_k[k] >> 4, upp = ct >> 4;   // unit index within a position, units per position
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                float sm = 0.0f, sq = 0.0f;
+                for (int l2 = 0; l2 < L; ++l2) sm += my_part[(2 * (l2 * upp + cu) + h8) * 256];
+                const float mu = sm / (float)L;
+                for (int l2 = 0; l2 < L; ++l2) {
+                  const float* pp = my_part + (2 * (l2 * upp + cu) + h8) * 256;
+                  const float d = pp[0] - mu;
+                  sq += pp[128] + 8.0f * d * d;
+                }
+                mean[k][h8] = mu;
+                rstd[k][h8] = rsqrtf(sq * inv_n + 1e-5f);
+              }
+            } else {
+              const int g0 = (c0_k[k] / cg) * cg;   // first channel (within the tile) of my group
+              const int upg = cg >> 4;              // units per (group, position)
+              int colg;                             // accumulator column of (position 0, channel g0)
+              int pos_step;                         // column step per position
+              if (a.half_layout) {
+                const int h = g0 >= (ct >> 1) ? 1 : 0;
+                colg = h * half_cols + (g0 - h * (ct >> 1));
+                pos_step = ct >> 1;
+              } else {
+                colg = g0;
+                pos_step = ct;
+              }
+              float sm = 0.0f, sq = 0.0f;
+              for (int l2 = 0; l2 < L; ++l2)
+                for (int j = 0; j < upg; ++j) sm += my_part[(((colg + l2 * pos_step) >> 4) + j) * 256];
+              const float mu = sm / (float)(L * upg);
+              for (int l2 = 0; l2 < L; ++l2)
+                for (int j = 0; j < upg; ++j) {
+                  const float* pp = my_part + (((colg + l2 * pos_step) >> 4) + j) * 256;
+                  const float d = pp[0] - mu;
+                  sq += pp[128] + 16.0f * d * d;
+                }
+              mean[k][0] = mean[k][1] = mu;
+              rstd[k][0] = rstd[k][1] = rsqrtf(sq * inv_n + 1e-5f);
+            }
+          }
+        }
+      }
+
+      // ---- normalise, Mish, time embedding, residual, hi/lo split, store: 8 channels (one 16-byte chunk) at a time ----
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int u = part + 4 * k;
+        if (u < n_units) {
+          const int lo = lo_k[k], c0 = c0_k[k];
+          const int kk = lo * a.cout + nt * ct + c0;            // K index (position-major) of the unit's first channel
+          const int chunk = (kk & (E::kCpc - 1)) >> 3;          // 16-byte chunk inside the 128-byte row
+          const int kr = lo * a.res.C + nt * ct + c0;
+          const size_t rsrc = ((size_t)rt * (L * (a.res.C >> E::kShift)) + (kr >> E::kShift)) * kTcBlockBytes;
+          const int chr = (kr & (E::kCpc - 1)) >> 3;
+          float y[16], r[16];
+          umma::tmem_ld16(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), y);
+          if (a.mode == TC_GN_RES_PW) umma::tmem_ld16(t_acc + (uint32_t)(a.ph[1].d_col + lo * ct + c0), r);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
+            if (a.mode == TC_GN_RES_ID) {
+              // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
+              const size_t off = rsrc + tc_swz_bytes(row_local, chr + m);
+              rh = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+              if (a.res.lo) rl = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
+            }
+            float v[8];
+            {
+              const float* pb0 = s_par + c0 + m * 8;
+              const float4 z0 = *reinterpret_cast<const float4*>(pb0), z1 = *reinterpret_cast<const float4*>(pb0 + 4);
+              const float bi[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(y[m * 8 + e], sc0, bi[e]);
+            }
+            if (a.mode != TC_BIAS) {
+              const float m_ = (two && m) ? mean[k][1] : mean[k][0], r_ = (two && m) ? rstd[k][1] : rstd[k][0];
+              const float* pg = s_par + 128 + c0 + m * 8;
+              const float4 g0 = *reinterpret_cast<const float4*>(pg), g1 = *reinterpret_cast<const float4*>(pg + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(pg + 128), b1 = *reinterpret_cast<const float4*>(pg + 132);
+              const float4 e0 = *reinterpret_cast<const float4*>(pg + 256), e1 = *reinterpret_cast<const float4*>(pg + 260);
+              const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = mish_fast((v[e] - m_) * r_ * ga[e] + be[e]) + te[e];
+            }
+            if (a.mode == TC_GN_RES_PW) {
+              const float* pb = s_par + 512 + c0 + m * 8;
+              const float4 q0 = *reinterpret_cast<const float4*>(pb), q1 = *reinterpret_cast<const float4*>(pb + 4);
+              const float br[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += fmaf(r[m * 8 + e], sc1, br[e]);
+            } else if (a.mode == TC_GN_RES_ID) {
+              float x[8];
+              tc_chunk_sum<EL>(rh, rl, a.res.lo != nullptr, x);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += x[e];
+            }
+            // hi/lo split of 8 values -> one 16-byte chunk each
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hh[e] = pack16x2<EL>(v[2 * e], v[2 * e + 1]);
+              const float2 hf = unpack16x2<EL>(hh[e]);
+              ll[e] = pack16x2<EL>(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+            }
+            if (grow < a.rows) {
+              size_t dst;
+              if (a.out_pm) {
+                // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
+                const int rby = 2 * a.cout, c = nt * ct + c0;
+                dst = ((size_t)((grow >> 3) * (L + 4) + lo + 2) * 8 + (grow & 7)) * rby +
+                      (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
+              } else {
+                dst = ((size_t)rt * (L * kch_out) + (kk >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(row_local, chunk + m);
+              }
+              *reinterpret_cast<uint4*>((uint8_t*)a.out_hi + dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              if (a.out_lo) *reinterpret_cast<uint4*>((uint8_t*)a.out_lo + dst) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          }
+        }
+      }
+      {
+        // every accumulator read of this tile is complete: hand the TMEM buffer back to the MMA warp
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + buf, 0); else umma::mbar_arrive(acc_empty + buf); }
+      }
+      if (dbg) t_busy += clock64() - t_start;
+      if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) fph ^= 1; } else { fph ^= 1; }
+    }
+    if (dbg && et == 0) { dbg[6] = w_full; dbg[8] = t_busy; }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (CG == 2) t2::cluster_sync_all();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else umma::tmem_dealloc<512>(tmem_base);
+  }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+}
+
+}  // namespace edmp

@@ -20,6 +20,7 @@
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv_pm.cuh"
+#include "conv_tc2.cuh"
 #include "edmp_b200.h"
 
 namespace edmp {
@@ -192,13 +193,14 @@ struct Act {
   bool ok = true;
 };
 
-enum LayerKind { LAYER_SIMT = 0, LAYER_TC = 1, LAYER_PACK = 2, LAYER_PM = 3, LAYER_PM_PACK = 4 };
+enum LayerKind { LAYER_SIMT = 0, LAYER_TC = 1, LAYER_PACK = 2, LAYER_PM = 3, LAYER_PM_PACK = 4, LAYER_TC2 = 5 };
 
 struct Layer {
   int kind = LAYER_SIMT;
   ConvLaunchFn fn = nullptr;
   ConvArgs args;
   TcArgs targs;                 // LAYER_TC
+  Tc2Args t2;                   // LAYER_TC2 (persistent kernel, conv_tc2.cuh)
   PmArgs pargs;                 // LAYER_PM
   bool pm_final = false;        // LAYER_PM: writes eps (the caller's buffer) through the fused final 1x1 conv
   int tc_tiles = 0;             // column tiles (grid.y) of a tensor-core layer
@@ -228,6 +230,8 @@ struct UNet {
   bool tc_16() const { return tc_el != TC_EL_TF32; }
   bool pm = false;        // position-major tensor-core kernels for the horizon 25 / 50 levels (16-bit elements)
   bool final_fused = false;   // final 1x1 conv fused into the last position-major layer
+  bool tc2 = false;           // persistent second-generation kernel (conv_tc2.cuh) for the rows-as-M levels
+  int sm_count = 148;
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   int max_rows = 0;
@@ -518,6 +522,52 @@ struct Builder {
     }
     t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
     ly.tc_smem = 1024 + t.stage_bytes + 1024;
+    if (u->tc2 && !t.out_plain && t.lout * t.ct <= 16 * kT2MaxUnits) finish_tc2_layer(ly, n_tiles);   // (25-position up-sampling stays on v1)
+  }
+
+  // persistent kernel (conv_tc2.cuh): same operand layouts and weight tiles as conv_tc.cuh
+  void finish_tc2_layer(Layer& ly, int n_tiles) {
+    const TcArgs& t = ly.targs;
+    Tc2Args& v = ly.t2;
+    std::memset(&v, 0, sizeof(Tc2Args));
+    v.n_phases = t.n_phases;
+    for (int p = 0; p < t.n_phases; ++p) {
+      const TcPhase& s = t.ph[p];
+      Tc2Phase& d = v.ph[p];
+      d.a = s.a; d.b = s.b; d.w_hi = s.w_hi; d.w_lo = s.w_lo; d.acc_scale = s.acc_scale;
+      d.lin = s.lin; d.slots = s.slots; d.d_col = s.d_col; d.col_step = t.ct;
+      uint32_t touched = 0;
+      for (int li = 0; li < s.lin; ++li) {
+        const TcSched& q = s.sched[li];
+        d.sched[li].slot_begin = q.slot_begin; d.sched[li].n_slots = q.n_slots; d.sched[li].lo_begin = q.lo_begin;
+        int n_acc = 0;
+        while (n_acc < q.n_slots && ((touched >> (q.lo_begin + n_acc)) & 1u)) ++n_acc;
+        for (int j = n_acc; j < q.n_slots; ++j) ok = ok && !((touched >> (q.lo_begin + j)) & 1u);   // touched positions form a prefix
+        d.sched[li].n_acc = (int8_t)n_acc;
+        for (int j = 0; j < q.n_slots; ++j) touched |= 1u << (q.lo_begin + j);
+      }
+    }
+    v.lout = t.lout; v.ct = t.ct; v.cout = t.cout; v.cg = t.cg; v.mode = t.mode; v.split = t.split;
+    const int cols = t.lout * t.ct;
+    ok = ok && cols <= 16 * kT2MaxUnits && (cols % 16) == 0 && t.ct <= 128;
+    v.acc_bufs = (t.n_phases == 1 && cols <= 256) ? 2 : 1;
+    v.acc_stride = 256;
+    v.half_layout = 0;
+    v.n_col_tiles = n_tiles;
+    v.bias = t.bias; v.gamma = t.gamma; v.beta = t.beta; v.bres = t.bres;
+    v.res = t.res; v.out_hi = t.out_hi; v.out_lo = t.out_lo; v.out_pm = t.out_pm;
+    const int nparts = t.split ? 2 : 1;
+    int max_slots = t.ph[0].slots;
+    if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
+    const size_t a_stage = (size_t)kTcBlockBytes * nparts;
+    const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
+    const size_t part_bytes = (size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) * 1024;   // GroupNorm pieces (mean, M2) per unit and row
+    const size_t budget = 232448 - 1024 - 4096 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
+    v.b_stages = (3 * b_stage + 3 * a_stage <= budget) ? 3 : ((2 * b_stage + 2 * a_stage <= budget) ? 2 : 1);
+    v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - v.b_stages * b_stage) / a_stage);
+    ok = ok && v.a_stages >= 2;
+    ly.kind = LAYER_TC2;
+    ly.tc_smem = 1024 + v.a_stages * a_stage + v.b_stages * b_stage + part_bytes;
   }
 
   static TcOperand operand(const Act* a) {
@@ -953,6 +1003,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -972,6 +1024,12 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   // precision != fp32; the long-horizon, few-channel levels run on the position-major tensor-core
   // kernel when the operand elements are 16-bit, else on the CUDA-core kernels.
   u->pm = u->tc && u->tc_16() && getenv("EDMP_NO_PM") == nullptr;
+  u->tc2 = u->pm && getenv("EDMP_TC_V1") == nullptr;
+  {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      u->sm_count = n;
+  }
   auto on_tc = [&](const Act& a) { return u->tc && a.L <= kTcMaxLin; };
   auto on_pm = [&](const Act& a) { return u->pm && a.L > kTcMaxLin; };
   if (u->pm) x = b.pm_pack_input(x);
@@ -1100,6 +1158,16 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     if (a.ra == input_act) a.ra = x;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     ly.fn(a, st);
+  } else if (ly.kind == LAYER_TC2) {
+    Tc2Args a = ly.t2;
+    a.rows = rows;
+    a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
+    a.dbg = u->dbg;
+    a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
+    const int n_tiles = a.n_row_tiles * a.n_col_tiles;
+    dim3 grid(std::min(n_tiles, u->sm_count));
+    if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
+    else launch_pdl(conv_tc2_kernel<TC_EL_BF16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
   } else if (ly.kind == LAYER_TC) {
     TcArgs a = ly.targs;
     a.rows = rows;
@@ -1177,10 +1245,12 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
 // debug: run op `op` alone `iters` times and return the clock64 stamps of its CTAs ([ctas][8])
 int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st) {
   EDMP_REQUIRE(op >= 0 && op < (int)u->layers.size() &&
-                   (u->layers[op].kind == LAYER_TC || u->layers[op].kind == LAYER_PM), "op is not a tensor-core layer");
+                   (u->layers[op].kind == LAYER_TC || u->layers[op].kind == LAYER_PM || u->layers[op].kind == LAYER_TC2),
+               "op is not a tensor-core layer");
   Layer& ly = u->layers[op];
   const int ctas = ly.kind == LAYER_PM ? ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt)
-                                       : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
+                   : ly.kind == LAYER_TC2 ? std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count)
+                                          : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;
   EDMP_CK(cudaMalloc(&d, (size_t)ctas * 16 * sizeof(long long)));
