@@ -70,6 +70,7 @@ struct Tc2Args {
   void *out_hi, *out_lo;          // tiled output (or position-major images when out_pm)
   int out_pm;
   long long* dbg;                 // optional [ctas][16] clock64 stamps / counters, normally null
+  int dbg_skip;                   // profiling experiments only (EDMP_T2_SKIP): 1 no stores, 2 no Mish, 4 no residual loads, 8 no combine
 };
 
 namespace t2 {
@@ -102,6 +103,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(umma::smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread, WITHOUT waiting: several loads can be in
+// flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait without the diagnostic printf of umma::mbar_wait in the hot loops (still bounded: traps instead of hanging)
 __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   __shared__ uint64_t pa_full[kT2MaxAStages], pb_full[kT2MaxBStages];   // CG = 2, leader: "the peer's stage is full"
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_par[5 * 128];            // bias | gamma | beta | temb | bres of this column tile
+  __shared__ __align__(16) float s_par2[2][5 * 128];        // bias | gamma | beta | temb | bres of a column tile (by tile parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? t2::cluster_ctarank() : 0u;
@@ -370,23 +382,30 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     const float sc0 = a.ph[0].acc_scale, sc1 = a.ph[1].acc_scale;
     const int kch_out = a.cout >> E::kShift;
     const int half_cols = (L * ct) >> 1;                  // half_layout: columns of one half
+    const int ct_log2 = 31 - __clz(ct);                   // ct is a power of two
     float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
+    const int n_pieces_alloc = n_units * (two ? 2 : 1);
+    float* my_stat = my_part + n_pieces_alloc * 256;   // [group][mean | rstd][128 rows]
+    const int n_groups = two ? (ct >> 3) : ct / cg;
+    const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (cg >> 4)));
     uint32_t buf = 0, fph = 0;
-    long long w_full = 0, t_busy = 0;
-    bool first_tile = true;
+    long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
+    int tile_par = 0;
     for (int t = unit0; t < n_tiles; t += n_walkers) {
       const int nt = t % a.n_col_tiles;
       const int rt = (t / a.n_col_tiles) * CG + (int)rank;
       const int grow = rt * kTcRows + row_local;
-      // ---- per-channel parameters of this column tile ----
-      if (!first_tile) t2::bar_epilogue();                // every reader of the previous tile's parameters is done
-      first_tile = false;
+      // ---- per-channel parameters of this column tile (double-buffered by tile parity: one barrier per tile) ----
+      const long long tp0 = dbg ? clock64() : 0;
+      float* s_par = s_par2[tile_par];
+      tile_par ^= 1;
       for (int e = et; e < 5 * ct; e += kT2EpiThreads) {
         const int which = e / ct, c = e - which * ct;
         const float* src = which == 0 ? a.bias : which == 1 ? a.gamma : which == 2 ? a.beta : which == 3 ? a.temb : a.bres;
         s_par[which * 128 + c] = src ? src[nt * ct + c] : (which == 1 ? 1.0f : 0.0f);
       }
-      t2::bar_epilogue();
+      t2::bar_epilogue();   // also: every thread is past the previous tile's reads of the GroupNorm pieces
+      if (dbg) t_par += clock64() - tp0;
       {
         const long long tw = dbg ? clock64() : 0;
         t2::wait(acc_full + buf, fph);
@@ -397,182 +416,215 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       umma::tc_fence_after();
       const uint32_t t_acc = t_lane + buf * (uint32_t)a.acc_stride;
 
-      // ---- my units: unit u = part + 4k covers accumulator columns [16u, 16u+16) ----
-      int lo_k[4], c0_k[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int col = (part + 4 * k) << 4;
+      // ---- my units: unit u = part + 4k covers accumulator columns [16u, 16u+16); two units per batch ----
+      // (position, first channel within the tile) of the unit at accumulator column `col`
+      auto unit_pos = [&](int col, int& lo, int& c0) {
         if (a.half_layout) {
           const int h = col >= half_cols ? 1 : 0, rem = col - h * half_cols;
-          lo_k[k] = rem / (ct >> 1);
-          c0_k[k] = h * (ct >> 1) + rem % (ct >> 1);
+          lo = rem >> (ct_log2 - 1);
+          c0 = h * (ct >> 1) + (rem & ((ct >> 1) - 1));
         } else {
-          lo_k[k] = col / ct;
-          c0_k[k] = col % ct;
+          lo = col >> ct_log2;
+          c0 = col & (ct - 1);
         }
-      }
-      float mean[4][2], rstd[4][2];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { mean[k][0] = mean[k][1] = 0.0f; rstd[k][0] = rstd[k][1] = 1.0f; }
+      };
       if (a.mode != TC_BIAS) {
         // GroupNorm(8) over (cg channels x L positions) of this row (blocks.py:24-26).  Every 16-column unit (8-column
         // half when groups have 8 channels) yields an exact two-pass (mean, M2) on registers; the pieces of a group
         // meet in shared memory among the four warps of this lane quarter and are combined with
         // M2 = sum M2_i + n_i * sum (mean_i - mean)^2 -- no E[x^2] - mean^2 cancellation anywhere.
+#pragma unroll 1
+        for (int kb = 0; kb < 4; kb += 2) {
+          if (part + 4 * kb >= n_units) break;
+          uint32_t raw[2][16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int u = part + 4 * k;
-          if (u < n_units) {
-            float v[16], b[16];
-            umma::tmem_ld16(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), v);
-            pm_ld_par16(s_par + c0_k[k], b);
-            float s0 = 0.0f, s1 = 0.0f;
+          for (int j = 0; j < 2; ++j)
+            if (part + 4 * (kb + j) < n_units)
+              t2::tmem_ld16_nowait(t_acc + (uint32_t)(a.ph[0].d_col + ((part + 4 * (kb + j)) << 4)), raw[j]);
+          t2::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = fmaf(v[i], sc0, b[i]);
-              if (i < 8) s0 += v[i]; else s1 += v[i];
-            }
-            const float m0 = two ? s0 * 0.125f : (s0 + s1) * 0.0625f, m1 = two ? s1 * 0.125f : m0;
-            float q0 = 0.0f, q1 = 0.0f;
+          for (int j = 0; j < 2; ++j) {
+            const int u = part + 4 * (kb + j);
+            if (u < n_units) {
+              int lo, c0;
+              unit_pos(u << 4, lo, c0);
+              float v[16], b[16];
+              pm_ld_par16(s_par + c0, b);
+              float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float d = v[i] - (i < 8 ? m0 : m1);
-              if (i < 8) q0 = fmaf(d, d, q0); else q1 = fmaf(d, d, q1);
-            }
-            if (two) {
-              my_part[(2 * u) * 256] = m0; my_part[(2 * u) * 256 + 128] = q0;
-              my_part[(2 * u + 1) * 256] = m1; my_part[(2 * u + 1) * 256 + 128] = q1;
-            } else {
-              my_part[u * 256] = m0; my_part[u * 256 + 128] = q0 + q1;
+              for (int i = 0; i < 16; ++i) {
+                v[i] = fmaf(__uint_as_float(raw[j][i]), sc0, b[i]);
+                if (i < 8) s0 += v[i]; else s1 += v[i];
+              }
+              const float m0 = two ? s0 * 0.125f : (s0 + s1) * 0.0625f, m1 = two ? s1 * 0.125f : m0;
+              float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float d = v[i] - (i < 8 ? m0 : m1);
+                if (i < 8) q0 = fmaf(d, d, q0); else q1 = fmaf(d, d, q1);
+              }
+              if (two) {
+                my_part[(2 * u) * 256] = m0; my_part[(2 * u) * 256 + 128] = q0;
+                my_part[(2 * u + 1) * 256] = m1; my_part[(2 * u + 1) * 256 + 128] = q1;
+              } else {
+                my_part[u * 256] = m0; my_part[u * 256 + 128] = q0 + q1;
+              }
             }
           }
+        }
+        const long long tb0 = dbg ? clock64() : 0;
+        if (dbg) t_stats += tb0 - t_start;
+        t2::bar_quarter(quarter);
+        // one thread per (row, group) combines the pieces; (mean, rstd) go back through shared memory
+        for (int g = part; g < n_groups; g += 4) {
+          int p0, pstep, cnt;       // first piece, piece step per position, pieces per position
+          float npiece;             // elements per piece
+          if (two) {
+            p0 = g; pstep = 2 * (ct >> 4); cnt = 1; npiece = 8.0f;
+          } else {
+            const int g0 = g * cg;
+            int colg;
+            if (a.half_layout) {
+              const int h = g0 >= (ct >> 1) ? 1 : 0;
+              colg = h * half_cols + (g0 - h * (ct >> 1));
+              pstep = ct >> 5;
+            } else {
+              colg = g0;
+              pstep = ct >> 4;
+            }
+            p0 = colg >> 4; cnt = cg >> 4; npiece = 16.0f;
+          }
+          float sm = 0.0f;
+          for (int l2 = 0; l2 < L; ++l2)
+            for (int q = 0; q < cnt; ++q) sm += my_part[(p0 + l2 * pstep + q) * 256];
+          const float mu = sm * inv_pieces;
+          float sq = 0.0f, sd = 0.0f;
+          for (int l2 = 0; l2 < L; ++l2)
+            for (int q = 0; q < cnt; ++q) {
+              const float* pp = my_part + (p0 + l2 * pstep + q) * 256;
+              const float d = pp[0] - mu;
+              sq += pp[128];
+              sd = fmaf(d, d, sd);
+            }
+          my_stat[g * 256] = mu;
+          my_stat[g * 256 + 128] = rsqrtf(fmaf(npiece, sd, sq) * inv_n + 1e-5f);
         }
         t2::bar_quarter(quarter);
+        if (dbg) t_bar += clock64() - tb0;
+      }
+      const long long tf0 = dbg ? clock64() : 0;
+
+      // ---- normalise, Mish, time embedding, residual, hi/lo split, store.  Every load of a batch (accumulator,
+      // residual accumulator, identity-residual operand blocks) is issued first; the group statistics are combined
+      // from the shared-memory pieces while those loads are in flight ----
+#pragma unroll 1
+      for (int kb = 0; kb < 4; ++kb) {
+        if (part + 4 * kb >= n_units) break;
+        uint32_t yr[1][16], rr[1][16];   // rr: residual accumulator, or the identity residual's hi (0..7) / lo (8..15) chunks
+        float mean[1][2], rstd[1][2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int u = part + 4 * k;
+        for (int j = 0; j < 1; ++j) {
+          const int u = part + 4 * (kb + j);
           if (u < n_units) {
-            if (two) {
-              // groups of 8 channels: the same half of the unit at this channel offset of every position
-              const int cu = c0_k[k] >> 4, upp = ct >> 4;   // unit index within a position, units per position
+            int lo, c0;
+            unit_pos(u << 4, lo, c0);
+            t2::tmem_ld16_nowait(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), yr[j]);
+            if (a.mode == TC_GN_RES_PW) t2::tmem_ld16_nowait(t_acc + (uint32_t)(a.ph[1].d_col + lo * ct + c0), rr[j]);
+            if (a.mode == TC_GN_RES_ID && !(a.dbg_skip & 4)) {
+              // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
+              const int kr = lo * a.res.C + nt * ct + c0;
+              const size_t rsrc = ((size_t)rt * (L * (a.res.C >> E::kShift)) + (kr >> E::kShift)) * kTcBlockBytes;
+              const int chr = (kr & (E::kCpc - 1)) >> 3;
 #pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                float sm = 0.0f, sq = 0.0f;
-                for (int l2 = 0; l2 < L; ++l2) sm += my_part[(2 * (l2 * upp + cu) + h8) * 256];
-                const float mu = sm / (float)L;
-                for (int l2 = 0; l2 < L; ++l2) {
-                  const float* pp = my_part + (2 * (l2 * upp + cu) + h8) * 256;
-                  const float d = pp[0] - mu;
-                  sq += pp[128] + 8.0f * d * d;
-                }
-                mean[k][h8] = mu;
-                rstd[k][h8] = rsqrtf(sq * inv_n + 1e-5f);
+              for (int m = 0; m < 2; ++m) {
+                const size_t off = rsrc + tc_swz_bytes(row_local, chr + m);
+                const uint4 qh = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+                const uint4 ql = a.res.lo ? *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off) : make_uint4(0, 0, 0, 0);
+                rr[j][4 * m] = qh.x; rr[j][4 * m + 1] = qh.y; rr[j][4 * m + 2] = qh.z; rr[j][4 * m + 3] = qh.w;
+                rr[j][8 + 4 * m] = ql.x; rr[j][8 + 4 * m + 1] = ql.y; rr[j][8 + 4 * m + 2] = ql.z; rr[j][8 + 4 * m + 3] = ql.w;
               }
-            } else {
-              const int g0 = (c0_k[k] / cg) * cg;   // first channel (within the tile) of my group
-              const int upg = cg >> 4;              // units per (group, position)
-              int colg;                             // accumulator column of (position 0, channel g0)
-              int pos_step;                         // column step per position
-              if (a.half_layout) {
-                const int h = g0 >= (ct >> 1) ? 1 : 0;
-                colg = h * half_cols + (g0 - h * (ct >> 1));
-                pos_step = ct >> 1;
-              } else {
-                colg = g0;
-                pos_step = ct;
-              }
-              float sm = 0.0f, sq = 0.0f;
-              for (int l2 = 0; l2 < L; ++l2)
-                for (int j = 0; j < upg; ++j) sm += my_part[(((colg + l2 * pos_step) >> 4) + j) * 256];
-              const float mu = sm / (float)(L * upg);
-              for (int l2 = 0; l2 < L; ++l2)
-                for (int j = 0; j < upg; ++j) {
-                  const float* pp = my_part + (((colg + l2 * pos_step) >> 4) + j) * 256;
-                  const float d = pp[0] - mu;
-                  sq += pp[128] + 16.0f * d * d;
-                }
-              mean[k][0] = mean[k][1] = mu;
-              rstd[k][0] = rstd[k][1] = rsqrtf(sq * inv_n + 1e-5f);
             }
           }
         }
-      }
-
-      // ---- normalise, Mish, time embedding, residual, hi/lo split, store: 8 channels (one 16-byte chunk) at a time ----
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int u = part + 4 * k;
-        if (u < n_units) {
-          const int lo = lo_k[k], c0 = c0_k[k];
-          const int kk = lo * a.cout + nt * ct + c0;            // K index (position-major) of the unit's first channel
-          const int chunk = (kk & (E::kCpc - 1)) >> 3;          // 16-byte chunk inside the 128-byte row
-          const int kr = lo * a.res.C + nt * ct + c0;
-          const size_t rsrc = ((size_t)rt * (L * (a.res.C >> E::kShift)) + (kr >> E::kShift)) * kTcBlockBytes;
-          const int chr = (kr & (E::kCpc - 1)) >> 3;
-          float y[16], r[16];
-          umma::tmem_ld16(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), y);
-          if (a.mode == TC_GN_RES_PW) umma::tmem_ld16(t_acc + (uint32_t)(a.ph[1].d_col + lo * ct + c0), r);
+        for (int j = 0; j < 1; ++j) {
+          mean[j][0] = mean[j][1] = 0.0f;
+          rstd[j][0] = rstd[j][1] = 1.0f;
+          const int u = part + 4 * (kb + j);
+          if (a.mode != TC_BIAS && u < n_units && !(a.dbg_skip & 8)) {
+            int lo, c0;
+            unit_pos(u << 4, lo, c0);
+            const int g = two ? (c0 >> 3) : c0 / cg;
+            mean[j][0] = my_stat[g * 256]; rstd[j][0] = my_stat[g * 256 + 128];
+            if (two) { mean[j][1] = my_stat[(g + 1) * 256]; rstd[j][1] = my_stat[(g + 1) * 256 + 128]; }
+          }
+        }
+        t2::tmem_ld_wait();
 #pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
-            if (a.mode == TC_GN_RES_ID) {
-              // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
-              const size_t off = rsrc + tc_swz_bytes(row_local, chr + m);
-              rh = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
-              if (a.res.lo) rl = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
-            }
-            float v[8];
-            {
-              const float* pb0 = s_par + c0 + m * 8;
-              const float4 z0 = *reinterpret_cast<const float4*>(pb0), z1 = *reinterpret_cast<const float4*>(pb0 + 4);
-              const float bi[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        for (int j = 0; j < 1; ++j) {
+          const int u = part + 4 * (kb + j);
+          if (u < n_units) {
+            int lo, c0;
+            unit_pos(u << 4, lo, c0);
+            const int kk = lo * a.cout + nt * ct + c0;            // K index (position-major) of the unit's first channel
+            const int chunk = (kk & (E::kCpc - 1)) >> 3;          // 16-byte chunk inside the 128-byte row
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaf(y[m * 8 + e], sc0, bi[e]);
-            }
-            if (a.mode != TC_BIAS) {
-              const float m_ = (two && m) ? mean[k][1] : mean[k][0], r_ = (two && m) ? rstd[k][1] : rstd[k][0];
-              const float* pg = s_par + 128 + c0 + m * 8;
-              const float4 g0 = *reinterpret_cast<const float4*>(pg), g1 = *reinterpret_cast<const float4*>(pg + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(pg + 128), b1 = *reinterpret_cast<const float4*>(pg + 132);
-              const float4 e0 = *reinterpret_cast<const float4*>(pg + 256), e1 = *reinterpret_cast<const float4*>(pg + 260);
-              const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-              const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            for (int m = 0; m < 2; ++m) {
+              float v[8];
+              {
+                const float* pb0 = s_par + c0 + m * 8;
+                const float4 z0 = *reinterpret_cast<const float4*>(pb0), z1 = *reinterpret_cast<const float4*>(pb0 + 4);
+                const float bi[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = mish_fast((v[e] - m_) * r_ * ga[e] + be[e]) + te[e];
-            }
-            if (a.mode == TC_GN_RES_PW) {
-              const float* pb = s_par + 512 + c0 + m * 8;
-              const float4 q0 = *reinterpret_cast<const float4*>(pb), q1 = *reinterpret_cast<const float4*>(pb + 4);
-              const float br[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += fmaf(r[m * 8 + e], sc1, br[e]);
-            } else if (a.mode == TC_GN_RES_ID) {
-              float x[8];
-              tc_chunk_sum<EL>(rh, rl, a.res.lo != nullptr, x);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += x[e];
-            }
-            // hi/lo split of 8 values -> one 16-byte chunk each
-            uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hh[e] = pack16x2<EL>(v[2 * e], v[2 * e + 1]);
-              const float2 hf = unpack16x2<EL>(hh[e]);
-              ll[e] = pack16x2<EL>(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-            }
-            if (grow < a.rows) {
-              size_t dst;
-              if (a.out_pm) {
-                // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
-                const int rby = 2 * a.cout, c = nt * ct + c0;
-                dst = ((size_t)((grow >> 3) * (L + 4) + lo + 2) * 8 + (grow & 7)) * rby +
-                      (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
-              } else {
-                dst = ((size_t)rt * (L * kch_out) + (kk >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(row_local, chunk + m);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(yr[j][m * 8 + e]), sc0, bi[e]);
               }
-              *reinterpret_cast<uint4*>((uint8_t*)a.out_hi + dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              if (a.out_lo) *reinterpret_cast<uint4*>((uint8_t*)a.out_lo + dst) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+              if (a.mode != TC_BIAS) {
+                const float m_ = (two && m) ? mean[j][1] : mean[j][0], r_ = (two && m) ? rstd[j][1] : rstd[j][0];
+                const float* pg = s_par + 128 + c0 + m * 8;
+                const float4 g0 = *reinterpret_cast<const float4*>(pg), g1 = *reinterpret_cast<const float4*>(pg + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(pg + 128), b1 = *reinterpret_cast<const float4*>(pg + 132);
+                const float4 e0 = *reinterpret_cast<const float4*>(pg + 256), e1 = *reinterpret_cast<const float4*>(pg + 260);
+                const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float z = (v[e] - m_) * (r_ * ga[e]) + be[e]; v[e] = ((a.dbg_skip & 2) ? z : mish_fast(z)) + te[e]; }
+              }
+              if (a.mode == TC_GN_RES_PW) {
+                const float* pb = s_par + 512 + c0 + m * 8;
+                const float4 q0 = *reinterpret_cast<const float4*>(pb), q1 = *reinterpret_cast<const float4*>(pb + 4);
+                const float br[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += fmaf(__uint_as_float(rr[j][m * 8 + e]), sc1, br[e]);
+              } else if (a.mode == TC_GN_RES_ID) {
+                float x[8];
+                tc_chunk_sum<EL>(make_uint4(rr[j][4 * m], rr[j][4 * m + 1], rr[j][4 * m + 2], rr[j][4 * m + 3]),
+                                 make_uint4(rr[j][8 + 4 * m], rr[j][8 + 4 * m + 1], rr[j][8 + 4 * m + 2], rr[j][8 + 4 * m + 3]),
+                                 a.res.lo != nullptr, x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += x[e];
+              }
+              // hi/lo split of 8 values -> one 16-byte chunk each
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hh[e] = pack16x2<EL>(v[2 * e], v[2 * e + 1]);
+                const float2 hf = unpack16x2<EL>(hh[e]);
+                ll[e] = pack16x2<EL>(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+              }
+              if (grow < a.rows && !(a.dbg_skip & 1)) {
+                size_t dst;
+                if (a.out_pm) {
+                  // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
+                  const int rby = 2 * a.cout, c = nt * ct + c0;
+                  dst = ((size_t)((grow >> 3) * (L + 4) + lo + 2) * 8 + (grow & 7)) * rby +
+                        (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
+                } else {
+                  dst = ((size_t)rt * (L * kch_out) + (kk >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(row_local, chunk + m);
+                }
+                *reinterpret_cast<uint4*>((uint8_t*)a.out_hi + dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                if (a.out_lo) *reinterpret_cast<uint4*>((uint8_t*)a.out_lo + dst) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+              }
             }
           }
         }
@@ -583,10 +635,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) { if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + buf, 0); else umma::mbar_arrive(acc_empty + buf); }
       }
-      if (dbg) t_busy += clock64() - t_start;
+      if (dbg) { const long long te = clock64(); t_busy += te - t_start; t_fin += te - tf0; }
       if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) fph ^= 1; } else { fph ^= 1; }
     }
-    if (dbg && et == 0) { dbg[6] = w_full; dbg[8] = t_busy; }
+    if (dbg && et == 0) { dbg[6] = w_full; dbg[8] = t_busy; dbg[9] = t_stats; dbg[10] = t_bar; dbg[11] = t_fin; dbg[12] = t_par; }
     umma::tc_fence_before();
   }
   __syncthreads();

@@ -561,8 +561,8 @@ struct Builder {
     if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
     const size_t a_stage = (size_t)kTcBlockBytes * nparts;
     const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
-    const size_t part_bytes = (size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) * 1024;   // GroupNorm pieces (mean, M2) per unit and row
-    const size_t budget = 232448 - 1024 - 4096 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
+    const size_t part_bytes = (size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) * 1024 + 8 * 1024;   // GroupNorm pieces (mean, M2) per unit and row
+    const size_t budget = 232448 - 1024 - 7168 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
     v.b_stages = (3 * b_stage + 3 * a_stage <= budget) ? 3 : ((2 * b_stage + 2 * a_stage <= budget) ? 2 : 1);
     v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - v.b_stages * b_stage) / a_stage);
     ok = ok && v.a_stages >= 2;
@@ -1003,8 +1003,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -1164,6 +1164,7 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
     a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
+    { static const int skip = getenv("EDMP_T2_SKIP") ? atoi(getenv("EDMP_T2_SKIP")) : 0; a.dbg_skip = skip; }
     const int n_tiles = a.n_row_tiles * a.n_col_tiles;
     dim3 grid(std::min(n_tiles, u->sm_count));
     if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
