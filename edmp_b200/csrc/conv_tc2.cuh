@@ -65,6 +65,7 @@ struct Tc2Args {
   int acc_bufs, acc_stride;       // TMEM accumulator buffers (1 or 2) and their column stride
   int half_layout;                // 1: phase-0 accumulator columns are [half][position][ct/2] (cta_group::2)
   int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
+  int ct_log2, cg_log2, nct_log2; // ct, cg and n_col_tiles are powers of two
   const float *bias, *gamma, *beta, *temb, *bres;
   TcOperand res;                  // identity residual source (tiled)
   void *out_hi, *out_lo;          // tiled output (or position-major images when out_pm)
@@ -121,6 +122,15 @@ __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 28)) __trap();
   }
 }
+// Mish = x * n / (n + 2), n = e^x (e^x + 2), with the single-instruction ex2 / rcp approximations (relative error
+// ~1e-7 each, below the split-MMA accumulation error).  Clamping x at 20 makes n / (n + 2) round to exactly 1.
+__device__ __forceinline__ float mish(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 20.0f) * 1.4426950408889634f));
+  const float n = e * (e + 2.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.0f));
+  return x * (n * r);
+}
 // non-blocking phase test
 __device__ __forceinline__ bool test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -144,7 +154,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   static_assert(EL != TC_EL_TF32, "conv_tc2 uses 16-bit operand elements");
   using E = TcElem<EL>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the array keeps the shared address space known to the compiler: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t a_full[kT2MaxAStages], a_empty[kT2MaxAStages], b_full[kT2MaxBStages], b_empty[kT2MaxBStages];
   __shared__ uint64_t pa_full[kT2MaxAStages], pb_full[kT2MaxBStages];   // CG = 2, leader: "the peer's stage is full"
   __shared__ uint64_t acc_full[2], acc_empty[2];
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           const TcOperand& op = first ? ph.a : ph.b;
           const int c2 = first ? cca : cca - ka;
           const int kop = first ? ka : kb;
-          const int rt = (ta / a.n_col_tiles) * CG + (int)rank;
+          const int rt = (ta >> a.nct_log2) * CG + (int)rank;
           const size_t blk = ((size_t)rt * (ph.lin * kop) + (size_t)lia * kop + c2) * kTcBlockBytes;
           umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
           uint8_t* dst = a_smem + as * a_stage_bytes;
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         if (tb < n_tiles && t2::test(b_empty + bs, bph ^ 1)) {
           const Tc2Phase& ph = a.ph[pb];
           const int kc = (ph.a.C + ph.b.C) >> E::kShift;
-          const int nt = tb % a.n_col_tiles;
+          const int nt = tb & (a.n_col_tiles - 1);
           const uint32_t wtile_bytes = (uint32_t)(ph.slots * ctl * 128);
           const size_t woff = (((size_t)nt * kc + ccb) * CG + rank) * wtile_bytes;
           umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes * (uint32_t)nparts);
@@ -382,27 +393,30 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     const float sc0 = a.ph[0].acc_scale, sc1 = a.ph[1].acc_scale;
     const int kch_out = a.cout >> E::kShift;
     const int half_cols = (L * ct) >> 1;                  // half_layout: columns of one half
-    const int ct_log2 = 31 - __clz(ct);                   // ct is a power of two
+    const int ct_log2 = a.ct_log2, cg_log2 = a.cg_log2;
     float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
     const int n_pieces_alloc = n_units * (two ? 2 : 1);
     float* my_stat = my_part + n_pieces_alloc * 256;   // [group][mean | rstd][128 rows]
-    const int n_groups = two ? (ct >> 3) : ct / cg;
+    const int n_groups = two ? (ct >> 3) : (ct >> cg_log2);
     const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (cg >> 4)));
     uint32_t buf = 0, fph = 0;
     long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
     int tile_par = 0;
     for (int t = unit0; t < n_tiles; t += n_walkers) {
-      const int nt = t % a.n_col_tiles;
-      const int rt = (t / a.n_col_tiles) * CG + (int)rank;
+      const int nt = t & (a.n_col_tiles - 1);
+      const int rt = (t >> a.nct_log2) * CG + (int)rank;
       const int grow = rt * kTcRows + row_local;
       // ---- per-channel parameters of this column tile (double-buffered by tile parity: one barrier per tile) ----
       const long long tp0 = dbg ? clock64() : 0;
       float* s_par = s_par2[tile_par];
       tile_par ^= 1;
-      for (int e = et; e < 5 * ct; e += kT2EpiThreads) {
-        const int which = e / ct, c = e - which * ct;
-        const float* src = which == 0 ? a.bias : which == 1 ? a.gamma : which == 2 ? a.beta : which == 3 ? a.temb : a.bres;
-        s_par[which * 128 + c] = src ? src[nt * ct + c] : (which == 1 ? 1.0f : 0.0f);
+      if (et < ct) {
+        const int c = nt * ct + et;
+        s_par[et] = a.bias[c];
+        s_par[128 + et] = a.gamma ? a.gamma[c] : 1.0f;
+        s_par[256 + et] = a.beta ? a.beta[c] : 0.0f;
+        s_par[384 + et] = a.temb ? a.temb[c] : 0.0f;
+        s_par[512 + et] = a.bres ? a.bres[c] : 0.0f;
       }
       t2::bar_epilogue();   // also: every thread is past the previous tile's reads of the GroupNorm pieces
       if (dbg) t_par += clock64() - tp0;
@@ -554,7 +568,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           if (a.mode != TC_BIAS && u < n_units && !(a.dbg_skip & 8)) {
             int lo, c0;
             unit_pos(u << 4, lo, c0);
-            const int g = two ? (c0 >> 3) : c0 / cg;
+            const int g = two ? (c0 >> 3) : (c0 >> cg_log2);
             mean[j][0] = my_stat[g * 256]; rstd[j][0] = my_stat[g * 256 + 128];
             if (two) { mean[j][1] = my_stat[(g + 1) * 256]; rstd[j][1] = my_stat[(g + 1) * 256 + 128]; }
           }
@@ -588,7 +602,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { const float z = (v[e] - m_) * (r_ * ga[e]) + be[e]; v[e] = ((a.dbg_skip & 2) ? z : mish_fast(z)) + te[e]; }
+                for (int e = 0; e < 8; ++e) { const float z = (v[e] - m_) * (r_ * ga[e]) + be[e]; v[e] = ((a.dbg_skip & 2) ? z : t2::mish(z)) + te[e]; }
               }
               if (a.mode == TC_GN_RES_PW) {
                 const float* pb = s_par + 512 + c0 + m * 8;

@@ -554,6 +554,9 @@ struct Builder {
     v.acc_stride = 256;
     v.half_layout = 0;
     v.n_col_tiles = n_tiles;
+    auto ilog2 = [](int x) { int l = 0; while ((1 << l) < x) ++l; return l; };
+    v.ct_log2 = ilog2(t.ct); v.cg_log2 = ilog2(t.cg); v.nct_log2 = ilog2(n_tiles);
+    ok = ok && (1 << v.ct_log2) == t.ct && (1 << v.cg_log2) == t.cg && (1 << v.nct_log2) == n_tiles;
     v.bias = t.bias; v.gamma = t.gamma; v.beta = t.beta; v.bres = t.bres;
     v.res = t.res; v.out_hi = t.out_hi; v.out_lo = t.out_lo; v.out_pm = t.out_pm;
     const int nparts = t.split ? 2 : 1;
