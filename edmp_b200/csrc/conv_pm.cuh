@@ -95,6 +95,15 @@ __device__ __forceinline__ void pm_epi_barrier() { asm volatile("bar.sync 2, %0;
 
 constexpr int kPmCt = 32;   // output channels per CTA (grid.y = cout / 32)
 
+// Mish = x * n / (n + 2), n = e^x (e^x + 2), single-instruction ex2 / rcp approximations (see conv_tc2.cuh)
+__device__ __forceinline__ float pm_mish(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 20.0f) * 1.4426950408889634f));
+  const float n = e * (e + 2.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.0f));
+  return x * (n * r);
+}
+
 __device__ __forceinline__ void pm_ld_par16(const float* p, float (&o)[16]) {   // 16 floats, 16-byte aligned shared memory
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) {
               const int g = u * GPU_ + i / CG;
               const float t = (v[i] - s_mr[0][row][g]) * s_mr[1][row][g] * ga[i] + be[i];
-              v[i] = mish_fast(t) + te[i];
+              v[i] = pm_mish(t) + te[i];
             }
           }
           if (!valid) continue;

@@ -550,7 +550,7 @@ struct Builder {
     v.lout = t.lout; v.ct = t.ct; v.cout = t.cout; v.cg = t.cg; v.mode = t.mode; v.split = t.split;
     const int cols = t.lout * t.ct;
     ok = ok && cols <= 16 * kT2MaxUnits && (cols % 16) == 0 && t.ct <= 128;
-    v.acc_bufs = (t.n_phases == 1 && cols <= 256) ? 2 : 1;
+    v.acc_bufs = ((t.n_phases == 1 && cols <= 256) || (t.n_phases == 2 && t.ph[1].d_col + cols <= 256)) ? 2 : 1;
     v.acc_stride = 256;
     v.half_layout = 0;
     v.n_col_tiles = n_tiles;
@@ -587,7 +587,10 @@ struct Builder {
     const int cin = xa.C + (xb ? xb->C : 0);
     const int L = xa.L;
     const int cg = cout / 8;
-    const int ct = std::max(16, cg);   // column tile: one GroupNorm group, or two when groups have 8 channels
+    // column tile: one GroupNorm group, or two when groups have 8 channels; the persistent kernel takes 32-channel
+    // tiles where 16 would leave the MMAs issue-bound (N = window x ct) and the accumulator still fits 256 columns
+    int ct = std::max(16, cg);
+    if (u->tc2 && ct < 32 && L * 32 <= 16 * kT2MaxUnits) ct = 32;
     Act y = new_act(u, out_name, cout, L, /*plain=*/false, /*tiled=*/true);
     ok = ok && y.ok;
     Layer ly;
@@ -658,7 +661,8 @@ struct Builder {
   Act tc_resample(const std::string& name, const Act& x, bool up, bool plain_out, bool pm_out = false) {
     const int C = x.C, L = x.L;
     const int lout = up ? ((2 * L == 8 || 2 * L == 14 || 2 * L == 26) ? 2 * L - 1 : 2 * L) : (L + 1) / 2;
-    const int ct = std::max(16, C / 8);
+    int ct = std::max(16, C / 8);
+    if (u->tc2 && ct < 32 && lout * 32 <= 16 * kT2MaxUnits && !plain_out) ct = 32;
     Act y = new_act(u, name, C, lout, plain_out, !plain_out && !pm_out, pm_out);
     ok = ok && y.ok;
     Layer ly;
