@@ -64,6 +64,7 @@ struct Tc2Args {
   int a_stages, b_stages;
   int acc_bufs, acc_stride;       // TMEM accumulator buffers (1 or 2) and their column stride
   int half_layout;                // 1: phase-0 accumulator columns are [half][position][ct/2] (cta_group::2)
+  int b_pad;                      // 1: weight stages are [zero slot][real slots][zero slot], neighbouring stages share a zero slot
   int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
   int ct_log2, cg_log2, nct_log2; // ct, cg and n_col_tiles are powers of two
   const float *bias, *gamma, *beta, *temb, *bres;
@@ -173,7 +174,16 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   const int b_stage_bytes = b_part_bytes * nparts;
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + a.a_stages * a_stage_bytes;
-  float* s_part = reinterpret_cast<float*>(b_smem + a.b_stages * b_stage_bytes);   // GroupNorm pieces [piece][mean | M2][128 rows]
+  // Weight stages.  Plain: [stage][hi | lo][max_slots x ctl rows].  Padded (full-window CTA-pair layers whose first
+  // and last tap slot are all zero): per part [Z][real slots of stage 0][Z][real slots of stage 1][Z]... -- the zero
+  // slots are written once, never copied, and shared by neighbouring stages; a stage's window view starts at its
+  // leading zero slot.
+  const int slot_bytes = ctl * 128;
+  const int b_stage_stride = a.b_pad ? (max_slots + 1) * slot_bytes : b_stage_bytes;
+  const int b_lo_off = a.b_pad ? (a.b_stages * (max_slots + 1) + 1) * slot_bytes : b_part_bytes;
+  const int b_real_off = a.b_pad ? slot_bytes : 0;
+  const int b_total_bytes = a.b_pad ? nparts * b_lo_off : a.b_stages * b_stage_bytes;
+  float* s_part = reinterpret_cast<float*>(b_smem + b_total_bytes);   // GroupNorm pieces [piece][mean | M2][128 rows]
   const int n_tiles = (a.n_row_tiles / CG) * a.n_col_tiles;
   const int unit0 = blockIdx.x / CG, n_walkers = gridDim.x / CG;
 
@@ -194,6 +204,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     } else {
       umma::tmem_alloc<512>(&tmem_slot);
     }
+  }
+  if (a.b_pad) {
+    // zero slots: one before every stage's real slots and one after the last stage, in both parts
+    const int nz = a.b_stages + 1, words = slot_bytes >> 4;
+    for (int i = threadIdx.x; i < nparts * nz * words; i += blockDim.x) {
+      const int w = i % words, z = (i / words) % nz, part_i = i / (words * nz);
+      reinterpret_cast<uint4*>(b_smem + part_i * b_lo_off + z * b_stage_stride)[w] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's operand reads
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -246,9 +265,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           const uint32_t wtile_bytes = (uint32_t)(ph.slots * ctl * 128);
           const size_t woff = (((size_t)nt * kc + ccb) * CG + rank) * wtile_bytes;
           umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes * (uint32_t)nparts);
-          uint8_t* dst = b_smem + bs * b_stage_bytes;
+          uint8_t* dst = b_smem + bs * b_stage_stride + b_real_off;
           umma::bulk_g2s(dst, (const uint8_t*)ph.w_hi + woff, wtile_bytes, b_full + bs);
-          if (a.split) umma::bulk_g2s(dst + b_part_bytes, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
+          if (a.split) umma::bulk_g2s(dst + b_lo_off, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
           if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
           if (++ccb == kc) {
             ccb = 0;
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
               if (CG == 2) t2::wait(pb_full + bs, bph);
               if (dbg) w_b += clock64() - tw;
             }
-            const uint32_t b_base = b0 + bs * (uint32_t)b_stage_bytes;
+            const uint32_t b_base = b0 + bs * (uint32_t)b_stage_stride;
             for (int li = 0; li < ph.lin; ++li) {
               const Tc2Sched s = ph.sched[li];
               if (s.n_slots == 0) continue;
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 const uint32_t d = acc0 + (uint32_t)(ph.d_col + (s.lo_begin + sl0) * ph.col_step);
                 const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + sl0) * ctl * 128);
                 const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
-                const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_part_bytes) & 0x3FFFF) >> 4);
+                const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_lo_off) & 0x3FFFF) >> 4);
                 const uint32_t accf = run == 0 ? 1u : 0u;
                 if (umma::elect_one()) {
 #pragma unroll
@@ -491,35 +510,37 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         t2::bar_quarter(quarter);
         // one thread per (row, group) combines the pieces; (mean, rstd) go back through shared memory
         for (int g = part; g < n_groups; g += 4) {
-          int p0, pstep, cnt;       // first piece, piece step per position, pieces per position
+          // the pieces of group g: for every position, `cnt` consecutive pieces from `p0` on, per segment (a group
+          // may straddle the two halves of the [half][position][ct/2] accumulator layout of a CTA pair)
+          int p0[2], cnt[2], pstep, nseg = 1;
           float npiece;             // elements per piece
           if (two) {
-            p0 = g; pstep = 2 * (ct >> 4); cnt = 1; npiece = 8.0f;
-          } else {
-            const int g0 = g * cg;
-            int colg;
-            if (a.half_layout) {
-              const int h = g0 >= (ct >> 1) ? 1 : 0;
-              colg = h * half_cols + (g0 - h * (ct >> 1));
-              pstep = ct >> 5;
-            } else {
-              colg = g0;
-              pstep = ct >> 4;
+            p0[0] = g; cnt[0] = 1; pstep = 2 * (ct >> 4); npiece = 8.0f;
+          } else if (a.half_layout) {
+            const int ch = ct >> 1, g0 = g << cg_log2, g1 = g0 + cg;
+            nseg = 0;
+            for (int h = 0; h < 2; ++h) {
+              const int cs = max(g0, h * ch), ce = min(g1, (h + 1) * ch);
+              if (cs < ce) { p0[nseg] = (h * half_cols + (cs - h * ch)) >> 4; cnt[nseg] = (ce - cs) >> 4; ++nseg; }
             }
-            p0 = colg >> 4; cnt = cg >> 4; npiece = 16.0f;
+            pstep = ch >> 4; npiece = 16.0f;
+          } else {
+            p0[0] = (g << cg_log2) >> 4; cnt[0] = cg >> 4; pstep = ct >> 4; npiece = 16.0f;
           }
           float sm = 0.0f;
-          for (int l2 = 0; l2 < L; ++l2)
-            for (int q = 0; q < cnt; ++q) sm += my_part[(p0 + l2 * pstep + q) * 256];
+          for (int sg = 0; sg < nseg; ++sg)
+            for (int l2 = 0; l2 < L; ++l2)
+              for (int q = 0; q < cnt[sg]; ++q) sm += my_part[(p0[sg] + l2 * pstep + q) * 256];
           const float mu = sm * inv_pieces;
           float sq = 0.0f, sd = 0.0f;
-          for (int l2 = 0; l2 < L; ++l2)
-            for (int q = 0; q < cnt; ++q) {
-              const float* pp = my_part + (p0 + l2 * pstep + q) * 256;
-              const float d = pp[0] - mu;
-              sq += pp[128];
-              sd = fmaf(d, d, sd);
-            }
+          for (int sg = 0; sg < nseg; ++sg)
+            for (int l2 = 0; l2 < L; ++l2)
+              for (int q = 0; q < cnt[sg]; ++q) {
+                const float* pp = my_part + (p0[sg] + l2 * pstep + q) * 256;
+                const float d = pp[0] - mu;
+                sq += pp[128];
+                sd = fmaf(d, d, sd);
+              }
           my_stat[g * 256] = mu;
           my_stat[g * 256 + 128] = rsqrtf(fmaf(npiece, sd, sq) * inv_n + 1e-5f);
         }

@@ -204,6 +204,8 @@ struct Layer {
   PmArgs pargs;                 // LAYER_PM
   bool pm_final = false;        // LAYER_PM: writes eps (the caller's buffer) through the fused final 1x1 conv
   int tc_tiles = 0;             // column tiles (grid.y) of a tensor-core layer
+  int cta_group = 1;            // LAYER_TC2: 2 = CTA pairs (cta_group::2)
+  int b_pad = 0;                // LAYER_TC2 pairs: weight stages with shared resident zero slots
   size_t tc_smem = 0;
   Act pack_src, pack_dst;       // LAYER_PACK
   int temb_off = -1;  // offset into the per-t time-embedding row, -1 = none
@@ -231,6 +233,7 @@ struct UNet {
   bool pm = false;        // position-major tensor-core kernels for the horizon 25 / 50 levels (16-bit elements)
   bool final_fused = false;   // final 1x1 conv fused into the last position-major layer
   bool tc2 = false;           // persistent second-generation kernel (conv_tc2.cuh) for the rows-as-M levels
+  bool cg2 = false;           // CTA pairs (cta_group::2) for the horizon 2 / 4 levels (large batches)
   int sm_count = 148;
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
@@ -283,7 +286,8 @@ static Act new_act(UNet* u, const std::string& name, int C, int L, bool plain = 
   }
   if (ok && tiled) {
     // row tiles of 128; zero-filled once so the padding rows of the last tile stay finite
-    const size_t n = (size_t)((u->max_rows + kTcRows - 1) / kTcRows) * L * (C / u->cpc()) * kTcBlockBytes;
+    // (an even number of row tiles: CTA pairs of the cta_group::2 layers own two row tiles each)
+    const size_t n = (size_t)(((u->max_rows + kTcRows - 1) / kTcRows + 1) & ~1) * L * (C / u->cpc()) * kTcBlockBytes;
     ok = cudaMalloc(&a.thi, n) == cudaSuccess;
     if (ok) { u->dev_allocs.push_back(a.thi); cudaMemset(a.thi, 0, n); }
     if (ok && u->tc_split) {
@@ -429,7 +433,7 @@ struct Builder {
   // have fp32's exponent range and use scale 1.
   template <class F>
   void pack_tc(int cout, int cin, int ct, int slots, F wfn, const void** hi_out, const void** lo_out,
-               float* acc_scale) {
+               float* acc_scale, int halves = 1) {
     const int cpc = u->cpc(), ebytes = u->tc_16() ? 2 : 4, epc = 16 / ebytes;
     const int n_tiles = cout / ct, kch = cin / cpc;
     float scale = 1.0f;
@@ -449,12 +453,15 @@ struct Builder {
     for (int nt = 0; nt < n_tiles; ++nt)
       for (int cc = 0; cc < kch; ++cc) {
         const size_t base = ((size_t)nt * kch + cc) * tile;
+        const int cth = ct / halves;   // halves == 2: [half][slot][ct/2 rows], each half is one CTA's share of the tile
         for (int sl = 0; sl < slots; ++sl)
           for (int c = 0; c < ct; ++c) {
-            const int r = sl * ct + c;
+            const int hf = c / cth;
+            const int r = sl * cth + (c - hf * cth);   // row inside the half
             for (int e = 0; e < cpc; ++e) {
               const float w = scale * wfn(nt * ct + c, cc * cpc + e, sl);
-              const size_t off = base + (size_t)r * 128 + ((((e / epc) ^ (r & 7)) << 4) | ((e % epc) * ebytes));
+              const size_t off = base + (size_t)hf * (tile / halves) + (size_t)r * 128 +
+                                 ((((e / epc) ^ (r & 7)) << 4) | ((e % epc) * ebytes));
               if (u->tc_el == TC_EL_F16) {
                 const uint16_t h = f16_round(w);
                 std::memcpy(&hi[off], &h, 2);
@@ -526,8 +533,9 @@ struct Builder {
   }
 
   // persistent kernel (conv_tc2.cuh): same operand layouts and weight tiles as conv_tc.cuh
-  void finish_tc2_layer(Layer& ly, int n_tiles) {
+  void finish_tc2_layer(Layer& ly, int n_tiles, int cgrp = 1) {
     const TcArgs& t = ly.targs;
+    ly.cta_group = cgrp;
     Tc2Args& v = ly.t2;
     std::memset(&v, 0, sizeof(Tc2Args));
     v.n_phases = t.n_phases;
@@ -535,7 +543,8 @@ struct Builder {
       const TcPhase& s = t.ph[p];
       Tc2Phase& d = v.ph[p];
       d.a = s.a; d.b = s.b; d.w_hi = s.w_hi; d.w_lo = s.w_lo; d.acc_scale = s.acc_scale;
-      d.lin = s.lin; d.slots = s.slots; d.d_col = s.d_col; d.col_step = t.ct;
+      d.lin = s.lin; d.slots = s.slots; d.col_step = (cgrp == 2 && p == 0) ? t.ct / 2 : t.ct;
+      d.d_col = cgrp == 2 ? p * 256 : s.d_col;
       uint32_t touched = 0;
       for (int li = 0; li < s.lin; ++li) {
         const TcSched& q = s.sched[li];
@@ -547,30 +556,36 @@ struct Builder {
         for (int j = 0; j < q.n_slots; ++j) touched |= 1u << (q.lo_begin + j);
       }
     }
-    v.lout = t.lout; v.ct = t.ct; v.cout = t.cout; v.cg = t.cg; v.mode = t.mode; v.split = t.split;
+    v.lout = t.lout; v.ct = t.ct; v.cout = t.cout; v.cg = t.cg; v.mode = t.mode; v.split = u->tc_split ? 1 : 0;
     const int cols = t.lout * t.ct;
     ok = ok && cols <= 16 * kT2MaxUnits && (cols % 16) == 0 && t.ct <= 128;
-    v.acc_bufs = ((t.n_phases == 1 && cols <= 256) || (t.n_phases == 2 && t.ph[1].d_col + cols <= 256)) ? 2 : 1;
+    v.acc_bufs = ((t.n_phases == 1 && cols <= 256) || (t.n_phases == 2 && cgrp == 1 && t.ph[1].d_col + cols <= 256)) ? 2 : 1;
     v.acc_stride = 256;
-    v.half_layout = 0;
+    v.half_layout = cgrp == 2 ? 1 : 0;
     v.n_col_tiles = n_tiles;
     auto ilog2 = [](int x) { int l = 0; while ((1 << l) < x) ++l; return l; };
     v.ct_log2 = ilog2(t.ct); v.cg_log2 = ilog2(t.cg); v.nct_log2 = ilog2(n_tiles);
     ok = ok && (1 << v.ct_log2) == t.ct && (1 << v.cg_log2) == t.cg && (1 << v.nct_log2) == n_tiles;
     v.bias = t.bias; v.gamma = t.gamma; v.beta = t.beta; v.bres = t.bres;
     v.res = t.res; v.out_hi = t.out_hi; v.out_lo = t.out_lo; v.out_pm = t.out_pm;
-    const int nparts = t.split ? 2 : 1;
+    const int nparts = u->tc_split ? 2 : 1;
     int max_slots = t.ph[0].slots;
     if (t.n_phases > 1 && t.ph[1].slots > max_slots) max_slots = t.ph[1].slots;
     const size_t a_stage = (size_t)kTcBlockBytes * nparts;
-    const size_t b_stage = (size_t)max_slots * t.ct * 128 * nparts;
-    const size_t part_bytes = (size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) * 1024 + 8 * 1024;   // GroupNorm pieces (mean, M2) per unit and row
+    const size_t slot_bytes = (size_t)(t.ct / cgrp) * 128;
+    v.b_pad = ly.b_pad;
+    // bytes of n weight stages (padded layout: per part n * (max_slots + 1) + 1 slots, see conv_tc2.cuh)
+    auto b_bytes = [&](int n) {
+      return ly.b_pad ? (size_t)nparts * ((size_t)n * (max_slots + 1) + 1) * slot_bytes : (size_t)n * max_slots * slot_bytes * nparts;
+    };
+    const size_t n_groups = t.cg == 8 ? t.ct / 8 : std::max(1, t.ct / t.cg);
+    const size_t part_bytes = ((size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) + n_groups) * 1024;   // GroupNorm pieces (mean, M2) per unit and row + group stats
     const size_t budget = 232448 - 1024 - 7168 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
-    v.b_stages = (3 * b_stage + 3 * a_stage <= budget) ? 3 : ((2 * b_stage + 2 * a_stage <= budget) ? 2 : 1);
-    v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - v.b_stages * b_stage) / a_stage);
+    v.b_stages = (b_bytes(3) + 3 * a_stage <= budget) ? 3 : ((b_bytes(2) + 2 * a_stage <= budget) ? 2 : 1);
+    v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - b_bytes(v.b_stages)) / a_stage);
     ok = ok && v.a_stages >= 2;
     ly.kind = LAYER_TC2;
-    ly.tc_smem = 1024 + v.a_stages * a_stage + v.b_stages * b_stage + part_bytes;
+    ly.tc_smem = 1024 + v.a_stages * a_stage + b_bytes(v.b_stages) + part_bytes;
   }
 
   static TcOperand operand(const Act* a) {
@@ -591,6 +606,10 @@ struct Builder {
     // tiles where 16 would leave the MMAs issue-bound (N = window x ct) and the accumulator still fits 256 columns
     int ct = std::max(16, cg);
     if (u->tc2 && ct < 32 && L * 32 <= 16 * kT2MaxUnits) ct = 32;
+    // cta_group::2 (CTA pairs sharing each weight tile) where every window can cover all L positions: L = 2, and
+    // L = 4 with one zero tap slot at either end; the accumulator is 256 columns per CTA
+    const bool pair = u->cg2 && (L == 2 || L == 4) && cout >= 256;
+    if (pair) ct = 256 / L;
     Act y = new_act(u, out_name, cout, L, /*plain=*/false, /*tiled=*/true);
     ok = ok && y.ok;
     Layer ly;
@@ -604,19 +623,28 @@ struct Builder {
     ph.a = operand(&xa);
     ph.b = operand(xb);
     ph.lin = L;
+    // slot s holds filter tap 4 - (j_begin + s); pairs pad the tap range so that every window spans all L positions
+    // (the two all-zero end slots of a padded pair layer are not stored in the weight tiles: the kernel keeps them
+    // resident in shared memory, Tc2Args::b_pad, and slot indices count from the leading zero slot)
+    const bool padded = pair && 2 + (L - 1) > 4;
     const int j_begin = std::max(0, 2 - (L - 1)), j_end = std::min(4, 2 + (L - 1));
+    const int j_view = padded ? -1 : j_begin;   // tap of view slot 0
     ph.slots = j_end - j_begin + 1;
     ph.d_col = 0;
+    ly.b_pad = padded ? 1 : 0;
     for (int li = 0; li < L; ++li) {
-      const int lo_min = std::max(0, li - 2), lo_max = std::min(L - 1, li + 2);
-      ph.sched[li].slot_begin = (int8_t)((lo_min - li + 2) - j_begin);
+      const int lo_min = pair ? 0 : std::max(0, li - 2), lo_max = pair ? L - 1 : std::min(L - 1, li + 2);
+      ph.sched[li].slot_begin = (int8_t)((lo_min - li + 2) - j_view);
       ph.sched[li].n_slots = (int8_t)(lo_max - lo_min + 1);
       ph.sched[li].lo_begin = (int8_t)lo_min;
     }
     const float* w = P(p + ".block.0.weight");   // [cout][cin][5]
     pack_tc(cout, cin, ct, ph.slots,
-            [&](int co, int ci, int sl) { return w[((size_t)co * cin + ci) * 5 + (4 - (j_begin + sl))]; },
-            &ph.w_hi, &ph.w_lo, &ph.acc_scale);
+            [&](int co, int ci, int sl) {
+              const int tap = 4 - (j_begin + sl);
+              return (tap >= 0 && tap <= 4) ? w[((size_t)co * cin + ci) * 5 + tap] : 0.0f;
+            },
+            &ph.w_hi, &ph.w_lo, &ph.acc_scale, pair ? 2 : 1);
     t.bias = vec(p + ".block.0.bias", cout);
     t.gamma = vec(p + ".block.2.weight", cout);
     t.beta = vec(p + ".block.2.bias", cout);
@@ -632,10 +660,10 @@ struct Builder {
       pr.lin = L;
       pr.slots = 1;
       pr.d_col = (L * ct <= 128) ? 128 : 256;
-      for (int li = 0; li < L; ++li) { pr.sched[li].slot_begin = 0; pr.sched[li].n_slots = 1; pr.sched[li].lo_begin = (int8_t)li; }
+      for (int li = 0; li < L; ++li) { pr.sched[li].slot_begin = (int8_t)(padded ? 1 : 0); pr.sched[li].n_slots = 1; pr.sched[li].lo_begin = (int8_t)li; }
       const float* wr = P(res_prefix + ".residual_conv.weight");   // [cout][rcin][1]
       pack_tc(cout, rcin, ct, 1, [&](int co, int ci, int) { return wr[(size_t)co * rcin + ci]; }, &pr.w_hi, &pr.w_lo,
-              &pr.acc_scale);
+              &pr.acc_scale, pair ? 2 : 1);
       t.bres = vec(res_prefix + ".residual_conv.bias", cout);
       macs += (double)L * rcin * cout;
     }
@@ -643,7 +671,8 @@ struct Builder {
     t.out_lo = y.tlo;
     ly.name = p;
     ly.macs_per_row = macs;
-    finish_tc_layer(ly, cout / ct);
+    if (pair) finish_tc2_layer(ly, cout / ct, 2);
+    else finish_tc_layer(ly, cout / ct);
     u->layers.push_back(ly);
     return y;
   }
@@ -1012,6 +1041,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -1032,6 +1063,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   // kernel when the operand elements are 16-bit, else on the CUDA-core kernels.
   u->pm = u->tc && u->tc_16() && getenv("EDMP_NO_PM") == nullptr;
   u->tc2 = u->pm && getenv("EDMP_TC_V1") == nullptr;
+  // pairs halve the number of schedulable tiles: only worth it when the batch still fills the machine
+  u->cg2 = u->tc2 && getenv("EDMP_NO_CG2") == nullptr && (max_rows >= 4096 || getenv("EDMP_CG2") != nullptr);
   {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
@@ -1172,6 +1205,14 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.dbg = u->dbg;
     a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
     { static const int skip = getenv("EDMP_T2_SKIP") ? atoi(getenv("EDMP_T2_SKIP")) : 0; a.dbg_skip = skip; }
+    if (ly.cta_group == 2) {
+      a.n_row_tiles = (a.n_row_tiles + 1) & ~1;
+      const int n_pair_tiles = (a.n_row_tiles / 2) * a.n_col_tiles;
+      dim3 grid(2 * std::min(n_pair_tiles, u->sm_count / 2));
+      if (u->tc_el == TC_EL_F16) launch_cluster(conv_tc2_kernel<TC_EL_F16, 2>, grid, dim3(kT2Threads), ly.tc_smem, st, 2, a);
+      else launch_cluster(conv_tc2_kernel<TC_EL_BF16, 2>, grid, dim3(kT2Threads), ly.tc_smem, st, 2, a);
+      return;
+    }
     const int n_tiles = a.n_row_tiles * a.n_col_tiles;
     dim3 grid(std::min(n_tiles, u->sm_count));
     if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
@@ -1257,7 +1298,8 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
                "op is not a tensor-core layer");
   Layer& ly = u->layers[op];
   const int ctas = ly.kind == LAYER_PM ? ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt)
-                   : ly.kind == LAYER_TC2 ? std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count)
+                   : ly.kind == LAYER_TC2 ? (ly.cta_group == 2 ? 2 * std::min(((((rows + kTcRows - 1) / kTcRows) + 1) / 2) * ly.t2.n_col_tiles, u->sm_count / 2)
+                                                               : std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count))
                                           : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;

@@ -38,7 +38,9 @@ for i in range(n_ops - 1):
     span = (t[:, 7].max() - t[:, 0].min())
     raw = buf[:n.value].astype(np.float64)
     if raw[:, 5].mean() > 0 and raw[:, 8].mean() > 0:   # persistent kernel (conv_tc2): counters instead of stamps
+        lead = raw[raw[:, 5] > 0]   # CTAs whose MMA warp issued (pair leaders / all CTAs of single-CTA layers)
         r = raw.mean(axis=0)
+        r[2:6] = lead[:, 2:6].mean(axis=0)
         print("%-36s ctas %4d  kernel %7.0f cyc (%5.1f us) | setup %5.0f  mma-warp total %7.0f  wait acc_empty %6.0f  wait W %6.0f  wait A %6.0f | epilogue busy %7.0f (stats %6.0f bar %6.0f final %6.0f) params %6.0f  wait acc_full %7.0f"
               % (lib.edmp_unet_op_name(h, i).decode(), n.value, r[7] - r[0], (r[7] - r[0]) / 1900.0, r[1] - r[0], r[5], r[2], r[3], r[4], r[8], r[9], r[10], r[11], r[12], r[6]))
         continue
