@@ -6,10 +6,12 @@
 
 A "step" is ONE pass of the hot path over one batch: the full 255-step guided reverse diffusion
 (TemporalUNet + posterior + guide gradient/update) of every trajectory row of the batch, followed
-by the per-row best-of-ensemble cost.  Workload (BASELINE.json configs[1]): per GPU
-one ensemble of the first ten shipped guides [1,2,3,4,5,9,10,11,12,13] x 102 rows = 1020
-trajectories (8 row tiles of 128; 8 GPUs: 8160 ~ the 8192 the config names), 20 synthetic obstacles, seeded random
-weights; weak scaling, ensembles rank-local, one NCCL all-gather of the per-row final costs.
+by the per-row best-of-ensemble cost.  Workload (BASELINE.json configs[1]): the
+"batch=8192 trajectories, guides [1..10]" ensemble fits one GPU, so at N = 1 it runs whole: the first
+ten shipped guides [1,2,3,4,5,9,10,11,12,13] x 819 rows = 8190 trajectories per GPU, 20 synthetic
+obstacles, seeded random weights.  Weak scaling: every rank runs its own ensemble of that size
+(ensembles are rank-local), one NCCL all-gather of the per-row final costs.  `--rows-per-guide 102`
+gives the 1/8 shard (1020 rows/GPU) of the strong-scaling reading of the same config.
 
 Prints ONE JSON line (rank 0).  `value` = trajectories/s with inputs resident in HBM;
 `e2e` = the same through the host-buffer C-ABI call (pinned host x_T in, trajectories + costs out).
@@ -30,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GUIDES = [1, 2, 3, 4, 5, 9, 10, 11, 12, 13]
-ROWS_PER_GUIDE = 102
+ROWS_PER_GUIDE = 819
 N_OBSTACLES = 20
 USEFUL_GFLOP_PER_ROW_STEP = 0.1222     # 61,096,192 non-padding MACs
 METRIC = "trajectories/sec (255-step, 50x7-DoF, guided ensemble)"
@@ -164,8 +166,8 @@ def workload_config(n_gpus, note=None, precision="fp32", rows_per_guide=None):
                        "T=255, horizon 50, 7 DoF" % (GUIDES, rpg, rows, rows * n_gpus, N_OBSTACLES),
            "rows_per_gpu": rows, "n_guides": len(GUIDES), "rows_per_guide": rpg,
            "obstacles": N_OBSTACLES, "precision_mode": precision, "parallelism": "dp%d (ensembles rank-local)" % n_gpus,
-           "l2": "working set per pass (114 MB weights + ~250 KB activations/row) exceeds the 126 MB L2; "
-                 "no explicit flush"}
+           "l2": "inputs larger than L2: one UNet forward streams ~57 MB of weight tiles and ~0.25 MB of "
+                 "activations per row (%.1f GB at this batch) through the 126 MB L2; no explicit flush" % (rows * 0.25e-3)}
     if note:
         cfg["note"] = note
     return cfg
@@ -284,26 +286,39 @@ def run_gpu_arm(args):
                                          ms.ctypes.data_as(ctypes.c_void_p), macs.ctypes.data_as(ctypes.c_void_p),
                                          ctypes.c_void_p(eps.data_ptr()), _lib.stream_ptr()), "edmp_unet_profile")
         names = [lib.edmp_unet_op_name(model.engine(rows), i).decode() for i in range(n_ops)]
-        top = int(np.argmax(ms))
+        kernels = [lib.edmp_unet_op_kernel(model.engine(rows), i).decode() for i in range(n_ops)]
+        # dominant kernel = the kernel (all its launches of one forward together) with the largest time share
+        share = {}
+        for k, m in zip(kernels, ms):
+            share[k] = share.get(k, 0.0) + float(m)
+        dom = max(share, key=share.get)
+        sel = np.array([k == dom for k in kernels])
+        top = int(np.argmax(np.where(sel, ms, 0.0)))
         peaks = load_peaks()
         prec = args.precision
         peak = peaks["bf16_tflops_sustained"] * (0.5 if prec in ("fp32", "tf32", "tf32x3") else 1.0)
-        achieved = 2.0 * macs[top] / (ms[top] * 1e-3) / 1e12
+        n_l = int(sel.sum())
+        achieved = 2.0 * macs[sel].sum() / (ms[sel].sum() * 1e-3) / 1e12     # useful FLOPs of its launches / their time
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(prec, {}).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": names[top], "achieved": achieved, "peak": peak,
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16 sustained%s (%s)" %
                                    (" x 0.5 (tf32-class operands)" if peak != peaks["bf16_tflops_sustained"] else "",
                                     peaks["source"]),
-                    "kernel_ms": float(ms[top]), "kernel_share_of_unet": float(ms[top] / ms.sum()),
-                    "useful_flops_per_launch": float(2.0 * macs[top])}
+                    "launches_per_forward": n_l, "kernel_ms": float(ms[sel].sum() / n_l),
+                    "kernel_share_of_unet": float(ms[sel].sum() / ms.sum()),
+                    "useful_flops_per_launch": float(2.0 * macs[sel].sum() / n_l),
+                    "note": "useful (non-padding, un-split) FLOPs; the hi/lo operand split issues 3x as many MMA FLOPs",
+                    "slowest_launch": {"op": names[top], "ms": float(ms[top]),
+                                       "achieved": float(2.0 * macs[top] / (ms[top] * 1e-3) / 1e12)},
+                    "by_kernel_ms": {k: round(v, 4) for k, v in share.items()}}
         if args.ops_out:
             with open(args.ops_out, "w") as f:
-                for nm, m, mc in zip(names, ms, macs):
-                    f.write("%-44s %9.1f us %8.2f useful TFLOP/s\n" % (nm, m * 1e3, 2 * mc / (m * 1e-3) / 1e12 if m > 0 else 0))
+                for nm, kn, m, mc in zip(names, kernels, ms, macs):
+                    f.write("%-44s %-14s %9.1f us %8.2f useful TFLOP/s\n" % (nm, kn, m * 1e3, 2 * mc / (m * 1e-3) / 1e12 if m > 0 else 0))
         unet_summary = {"ms_per_forward": float(ms.sum()), "useful_tflops": float(2.0 * macs.sum() / (ms.sum() * 1e-3) / 1e12),
                         "launches": int(n_ops)}
 
@@ -311,9 +326,9 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = torch.get_num_threads()
-        crow, cdt = cpu_sample(1, sd)
+        crow, cdt = cpu_sample(2, sd)
         cpu_baseline = {"value": crow / cdt, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                        "sample": "%d rows (10 guides x 1) x 255 steps, %d obstacles, %.1f s; oracle port "
+                        "sample": "%d rows (10 guides x 2) x 255 steps, %d obstacles, %.1f s; oracle port "
                                   "(torch CPU fp32 UNet + autograd guide)" % (crow, N_OBSTACLES, cdt)}
 
     if rank == 0:
@@ -338,8 +353,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "tf32x3"),
-                    help="fp32 (CUDA cores) | tf32x3 (tcgen05, 3xTF32, parity grade) | tf32 (tcgen05 single pass)")
+    ap.add_argument("--precision", default=os.environ.get("EDMP_PRECISION", "f16x3"),
+                    help="f16x3 (tcgen05, IEEE-half hi/lo split, parity grade, default) | tf32x3 | fp32 (CUDA cores) | "
+                         "bf16x3 / f16 / bf16 / tf32 (not parity grade)")
     ap.add_argument("--rows-per-guide", type=int, default=ROWS_PER_GUIDE,
                     help="trajectory rows per guide per GPU (x %d guides = rows per GPU)" % len(GUIDES))
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -23,6 +23,7 @@ SIGNATURES = {
     "edmp_unet_read_activation": (c_int, [c_void_p, c_char_p, c_int, c_void_p, P(c_int), P(c_int), c_void_p]),
     "edmp_unet_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "edmp_unet_op_name": (c_char_p, [c_void_p, c_int]),
+    "edmp_unet_op_kernel": (c_char_p, [c_void_p, c_int]),
     "edmp_unet_tc_trace": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, P(c_int), c_void_p]),
     "edmp_unet_precision": (c_int, [c_void_p]),
     "edmp_unet_launches_per_forward": (c_int, [c_void_p]),

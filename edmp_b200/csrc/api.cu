@@ -76,6 +76,7 @@ int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max
   EDMP_TRY(unet_tc_trace(u->impl, op, rows, out_h, max_ctas, n_ctas, (cudaStream_t)stream));
 }
 const char* edmp_unet_op_name(const edmp_unet* u, int i) { return u ? unet_op_name(u->impl, i) : nullptr; }
+const char* edmp_unet_op_kernel(const edmp_unet* u, int i) { return u ? unet_op_kernel(u->impl, i) : nullptr; }
 int edmp_unet_precision(const edmp_unet* u) { return u ? unet_precision(u->impl) : -1; }
 int edmp_unet_launches_per_forward(const edmp_unet* u) { return u ? unet_launches(u->impl) : 0; }
 

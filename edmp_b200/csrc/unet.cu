@@ -1324,6 +1324,19 @@ const char* unet_op_name(const UNet* u, int i) {
   return i == (int)u->layers.size() ? "final_conv.1" : u->layers[i].name.c_str();
 }
 
+const char* unet_op_kernel(const UNet* u, int i) {
+  if (i < 0 || i > (int)u->layers.size()) return nullptr;
+  if (i == (int)u->layers.size()) return "final_pw";
+  const Layer& ly = u->layers[i];
+  switch (ly.kind) {
+    case LAYER_TC2: return ly.cta_group == 2 ? "conv_tc2_pair" : "conv_tc2";
+    case LAYER_TC: return "conv_tc";
+    case LAYER_PM: return "conv_pm";
+    case LAYER_SIMT: return "conv_simt";
+    default: return "pack";
+  }
+}
+
 int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C, int* L, cudaStream_t st) {
   auto it = u->acts.find(name);
   EDMP_REQUIRE(it != u->acts.end(), std::string("unknown activation name: ") + name);

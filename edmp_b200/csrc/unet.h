@@ -15,6 +15,7 @@ int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C
 int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms, double* macs, float* eps,
                  cudaStream_t st);
 const char* unet_op_name(const UNet* u, int i);
+const char* unet_op_kernel(const UNet* u, int i);
 int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st);
 int unet_precision(const UNet* u);
 int unet_launches(const UNet* u);

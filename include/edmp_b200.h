@@ -80,8 +80,10 @@ int edmp_unet_read_activation(edmp_unet* u, const char* name, int rows, float* o
 int edmp_unet_profile(edmp_unet* u, const float* x_d, int t, int rows, int iters, float* ms_h,
                       double* macs_h, float* eps_d, void* stream);
 const char* edmp_unet_op_name(const edmp_unet* u, int i);
-/* debug: SM-clock stamps ([ctas][8]: entry, setup done, first weights, first activations, last MMA
- * issued, accumulator ready, epilogue done, exit) of tensor-core op `op` run alone */
+/* which kernel runs op i: "conv_tc2" (persistent tcgen05 kernel, single CTAs), "conv_tc2_pair" (cta_group::2 CTA
+ * pairs), "conv_tc", "conv_pm", "conv_simt", "pack", "final_pw" */
+const char* edmp_unet_op_kernel(const edmp_unet* u, int i);
+/* debug: SM-clock stamps / counters ([ctas][16], see tools/tc_trace.py) of tensor-core op `op` run alone */
 int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas,
                        void* stream);
 int edmp_unet_precision(const edmp_unet* u);

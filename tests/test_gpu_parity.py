@@ -101,6 +101,36 @@ def test_unet_rows_independent_at_full_batch(model):
     assert torch.equal(dup, dup[:1].expand_as(dup))
 
 
+@pytest.mark.parametrize("rows", [130, 300])
+def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, monkeypatch):
+    """The cta_group::2 path of the horizon 2 / 4 levels (normally chosen for batches >= 4096 rows), forced at a
+    size the oracle finishes in seconds; 300 rows = three row tiles, i.e. a pair with a padding tile."""
+    monkeypatch.setenv("EDMP_CG2", "1")
+    for prec in [p for p in PRECISIONS if p in ("f16x3", "bf16x3")]:
+        m = _model(tmp_path_factory, sd, prec)
+        x = torch.randn(rows, 7, 50, generator=torch.Generator().manual_seed(rows)) * 1.5
+        with torch.no_grad():
+            ref = unet_oracle.unet_forward(sd, x, 77).numpy()
+        eps = m(x.to(DEV), 77).cpu().numpy()
+        assert np.abs(eps - ref).max() <= EPS_TOL[prec]
+
+
+def test_unet_headline_batch_matches_small_batch(tmp_path_factory, sd):
+    """8190 rows (the bench workload: persistent tile walk, CTA pairs chosen automatically): rows spread over the
+    batch equal the same rows run through a small engine, and against the oracle."""
+    for prec in [p for p in PRECISIONS if p in ("f16x3",)]:
+        big, small = _model(tmp_path_factory, sd, prec), _model(tmp_path_factory, sd, prec)
+        x = torch.randn(8190, 7, 50, generator=torch.Generator().manual_seed(11)) * 1.5
+        full = big(x.to(DEV), 200)
+        idx = torch.tensor([0, 1, 127, 128, 4095, 4096, 8063, 8189])
+        part = small(x[idx].contiguous().to(DEV), 200)
+        assert (full[idx.to(DEV)] - part).abs().max().item() <= 2e-5
+        with torch.no_grad():
+            ref = unet_oracle.unet_forward(sd, x[idx], 200).numpy()
+        assert np.abs(full[idx.to(DEV)].cpu().numpy() - ref).max() <= EPS_TOL[prec]
+        assert torch.isfinite(full).all()
+
+
 def test_unet_rejects_bad_arguments(model):
     from edmp_b200 import _lib
     with pytest.raises(ValueError):
