@@ -31,10 +31,10 @@
 
 namespace edmp {
 
-constexpr int kT2EpiWarp0 = 2;                       // warp 0: operand producer, 1: TMEM + MMA issue
+constexpr int kT2EpiWarp0 = 3;                       // warp 0: operand producer, 1 (+TMEM) and 2: MMA issue
 constexpr int kT2EpiWarps = 16;
 constexpr int kT2EpiThreads = kT2EpiWarps * 32;
-constexpr int kT2Threads = (kT2EpiWarp0 + kT2EpiWarps) * 32;   // 576
+constexpr int kT2Threads = (kT2EpiWarp0 + kT2EpiWarps) * 32;   // 608
 constexpr int kT2MaxAStages = 4, kT2MaxBStages = 3;
 constexpr int kT2MaxUnits = 16;                      // accumulator columns per tile <= 256
 
@@ -64,6 +64,7 @@ struct Tc2Args {
   int a_stages, b_stages;
   int acc_bufs, acc_stride;       // TMEM accumulator buffers (1 or 2) and their column stride
   int half_layout;                // 1: phase-0 accumulator columns are [half][position][ct/2] (cta_group::2)
+  int mma_warps;                  // 1 or 2 MMA-issuing warps (2: alternate steps, see the kernel)
   int b_pad;                      // 1: weight stages are [zero slot][real slots][zero slot], neighbouring stages share a zero slot
   int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
   int ct_log2, cg_log2, nct_log2; // ct, cg and n_col_tiles are powers of two
@@ -147,6 +148,9 @@ __device__ __forceinline__ bool test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bar_quarter(int quarter) {   // the four epilogue warps sharing a TMEM lane quarter
   asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
 }
+// token passing between the two MMA-issuing warps (named barriers 6 and 7, 64 threads: one warp arrives, the other syncs)
+__device__ __forceinline__ void token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(6 + id) : "memory"); }
+__device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(6 + id) : "memory"); }
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 5, %0;" ::"n"(kT2EpiThreads) : "memory"); }
 }  // namespace t2
 
@@ -193,8 +197,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); umma::mbar_init(pa_full + i, 1); }
-    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, 1); umma::mbar_init(pb_full + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, 1); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
+    // (with two issuing warps each commits the weight stage / the accumulator after its own last step)
+    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, a.mma_warps); umma::mbar_init(pb_full + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, a.mma_warps); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
     umma::fence_barrier_init();
   }
   if (warp == 1) {
@@ -276,10 +281,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
     uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    const int mw = warp - 1, nw = a.mma_warps;   // issuing warp index, number of issuing warps
     if (CG == 2 && rank == 1) {
       // ===== peer of a CTA pair: relay "my stage is full" to the leader, which issues the MMAs for both =====
+      if (mw == 0)
       for (int t = unit0; t < n_tiles; t += n_walkers) {
         for (int p = 0; p < a.n_phases; ++p) {
           const Tc2Phase& ph = a.ph[p];
@@ -299,12 +306,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           }
         }
       }
-    } else {
-      // ===== MMA issuer: warp-uniform walk, one elected lane issues =====
+    } else if (mw < nw) {
+      // ===== MMA issuer: warp-uniform walk, one elected lane issues.  With two issuing warps the steps (one
+      // activation block = 12 MMAs) alternate between them: while one warp sits in its (blocking) MMA issue the
+      // other already waits for the next stage and builds its descriptors, so that per-step overhead leaves the
+      // tensor pipe's critical path (profiles/micro/r1_mma_pipe.txt).  A token (named barrier + tcgen05 fences)
+      // keeps the issue order identical to the single-warp order. =====
       const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
       const uint64_t desc0 = umma::make_desc_sw128(0);
       uint32_t buf = 0, eph = 0;   // accumulator buffer and the parity of its "empty" barrier
+      uint32_t step = 0;
       long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0;
+      if (nw == 2 && mw == 1) t2::token_pass(0);   // the first token
       for (int t = unit0; t < n_tiles; t += n_walkers) {
         {
           const long long tw = dbg ? clock64() : 0;
@@ -324,79 +337,81 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
               if (dbg) w_b += clock64() - tw;
             }
             const uint32_t b_base = b0 + bs * (uint32_t)b_stage_stride;
-            for (int li = 0; li < ph.lin; ++li) {
+            const bool last_chunk = (p == a.n_phases - 1) && (cc == kc - 1);
+            for (int li = 0; li < ph.lin; ++li, ++step) {
               const Tc2Sched s = ph.sched[li];
-              if (s.n_slots == 0) continue;
-              {
-                const long long tw = dbg ? clock64() : 0;
-                t2::wait(a_full + as, aph);
-                if (CG == 2) t2::wait(pa_full + as, aph);
-                if (dbg) w_a += clock64() - tw;
-              }
-              const uint32_t a_base = a0 + as * (uint32_t)a_stage_bytes;
-              const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
-              const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
-              // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are
-              // written for the first time -> two runs with their own accumulate flag; afterwards one run
-              const int n_first = (cc == 0) ? s.n_acc : s.n_slots;
-              const bool last_li_of_chunk = false;
-              (void)last_li_of_chunk;
+              if (s.n_slots == 0) continue;   // (never with two issuing warps, the host checks)
+              const bool mine = nw == 1 || (int)(step & 1) == mw;
+              if (mine) {
+                {
+                  const long long tw = dbg ? clock64() : 0;
+                  t2::wait(a_full + as, aph);
+                  if (CG == 2) t2::wait(pa_full + as, aph);
+                  if (dbg) w_a += clock64() - tw;
+                }
+                const uint32_t a_base = a0 + as * (uint32_t)a_stage_bytes;
+                const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+                const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+                // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are
+                // written for the first time -> two runs with their own accumulate flag; afterwards one run
+                const int n_first = (cc == 0) ? s.n_acc : s.n_slots;
+                const bool my_last_in_chunk = nw == 1 ? (li == ph.lin - 1) : (li >= ph.lin - 2);
+                if (nw == 2) { t2::token_wait(mw); umma::tc_fence_after(); }
 #pragma unroll 1
-              for (int run = 0; run < 2; ++run) {
-                const int sl0 = run == 0 ? 0 : n_first;
-                const int n = run == 0 ? n_first : s.n_slots - n_first;
-                if (n <= 0) continue;
-                const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows * CG, n * a.ct);
-                const uint32_t d = acc0 + (uint32_t)(ph.d_col + (s.lo_begin + sl0) * ph.col_step);
-                const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + sl0) * ctl * 128);
-                const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
-                const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_lo_off) & 0x3FFFF) >> 4);
-                const uint32_t accf = run == 0 ? 1u : 0u;
-                if (umma::elect_one()) {
+                for (int run = 0; run < 2; ++run) {
+                  const int sl0 = run == 0 ? 0 : n_first;
+                  const int n = run == 0 ? n_first : s.n_slots - n_first;
+                  if (n <= 0) continue;
+                  const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows * CG, n * a.ct);
+                  const uint32_t d = acc0 + (uint32_t)(ph.d_col + (s.lo_begin + sl0) * ph.col_step);
+                  const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + sl0) * ctl * 128);
+                  const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
+                  const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_lo_off) & 0x3FFFF) >> 4);
+                  const uint32_t accf = run == 0 ? 1u : 0u;
+                  if (umma::elect_one()) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
-                    const uint32_t acc = accf | (uint32_t)(ks > 0);
-                    if (CG == 2) {
-                      if (a.split) {
-                        t2::mma_f16_cg2(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
+                      const uint32_t acc = accf | (uint32_t)(ks > 0);
+                      if (CG == 2) {
+                        if (a.split) {
+                          t2::mma_f16_cg2(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                        } else {
+                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                        }
                       } else {
-                        t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                      }
-                    } else {
-                      if (a.split) {
-                        umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                        umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                        umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
-                      } else {
-                        umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                        if (a.split) {
+                          umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                          umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                          umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                        } else {
+                          umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                        }
                       }
                     }
                   }
+                  __syncwarp();
+                }
+                if (umma::elect_one()) {
+                  // frees the A stage (in both CTAs of a pair) once these MMAs have read it; after this warp's last
+                  // step of the chunk / the tile also the weight stage / the accumulator
+                  if (CG == 2) t2::commit_cg2(a_empty + as); else umma::mma_commit(a_empty + as);
+                  if (my_last_in_chunk) { if (CG == 2) t2::commit_cg2(b_empty + bs); else umma::mma_commit(b_empty + bs); }
+                  if (my_last_in_chunk && last_chunk) { if (CG == 2) t2::commit_cg2(acc_full + buf); else umma::mma_commit(acc_full + buf); }
                 }
                 __syncwarp();
+                if (nw == 2) { umma::tc_fence_before(); t2::token_pass(mw ^ 1); }
               }
-              if (umma::elect_one()) {   // frees the A stage (in both CTAs of a pair) once these MMAs have read it
-                if (CG == 2) t2::commit_cg2(a_empty + as); else umma::mma_commit(a_empty + as);
-              }
-              __syncwarp();
               if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
             }
-            if (umma::elect_one()) {
-              if (CG == 2) t2::commit_cg2(b_empty + bs); else umma::mma_commit(b_empty + bs);
-            }
-            __syncwarp();
             if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
           }
         }
-        if (umma::elect_one()) {
-          if (CG == 2) t2::commit_cg2(acc_full + buf); else umma::mma_commit(acc_full + buf);
-        }
-        __syncwarp();
         if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) eph ^= 1; } else { eph ^= 1; }
       }
-      if (dbg && lane == 0) { dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = w_a; dbg[5] = clock64() - t_begin; }
+      if (nw == 2 && (int)(step & 1) == mw) t2::token_wait(mw);   // consume the last token
+      if (dbg && lane == 0 && mw == 0) { dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = w_a; dbg[5] = clock64() - t_begin; }
     }
   } else {
     // ===== epilogue: 16 warps; a thread owns one accumulator lane (trajectory row) and every 4th 16-column unit =====

@@ -574,6 +574,16 @@ struct Builder {
     const size_t a_stage = (size_t)kTcBlockBytes * nparts;
     const size_t slot_bytes = (size_t)(t.ct / cgrp) * 128;
     v.b_pad = ly.b_pad;
+    {
+      // two MMA-issuing warps need every input position used and at least two steps per chunk (EDMP_MMA_WARPS=1: one)
+      bool all = true;
+      for (int p = 0; p < t.n_phases; ++p) {
+        all = all && t.ph[p].lin >= 2;
+        for (int li = 0; li < t.ph[p].lin; ++li) all = all && t.ph[p].sched[li].n_slots > 0;
+      }
+      static const int want = getenv("EDMP_MMA_WARPS") ? atoi(getenv("EDMP_MMA_WARPS")) : 2;
+      v.mma_warps = (all && want == 2) ? 2 : 1;
+    }
     // bytes of n weight stages (padded layout: per part n * (max_slots + 1) + 1 slots, see conv_tc2.cuh)
     auto b_bytes = [&](int n) {
       return ly.b_pad ? (size_t)nparts * ((size_t)n * (max_slots + 1) + 1) * slot_bytes : (size_t)n * max_slots * slot_bytes * nparts;
