@@ -378,3 +378,24 @@ def test_row0_noise_quirk_at_t1(model02):
     d = (x - xz)[:, :, 1:-1].cpu().numpy()
     assert np.all(d[0] == 0.0)
     np.testing.assert_allclose(d[1:], diff.beta[0], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# entry point (BASELINE config 1: infer_serial.py -c <derived cfg>, one synthetic scene, guide [1] x 4 rows)
+# ------------------------------------------------------------------------------------------------
+def test_infer_serial_entry_point(capsys):
+    import infer_serial
+    from edmp_b200 import synthetic
+    cfg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmark", "cfgs",
+                       "cfg_c1_synthetic.yaml")
+    np.random.seed(0)
+    r1 = infer_serial.main(["-c", cfg])
+    np.random.seed(0)
+    r2 = infer_serial.main(["-c", cfg])
+    assert len(r1) == 1
+    best, goal = r1[0]["trajectory"], r1[0]["goal"]
+    assert best.shape == (7, 50) and r1[0]["trajectories"].shape == (4, 7, 50)
+    assert np.array_equal(best[:, 0], synthetic.START) and np.array_equal(best[:, -1], goal)
+    assert np.isfinite(r1[0]["trajectories"]).all()
+    assert np.array_equal(r1[0]["trajectories"], r2[0]["trajectories"])       # same numpy draws -> same bits
+    assert "Success:" in capsys.readouterr().out

@@ -99,3 +99,33 @@ def test_unet_checkpoint_roundtrip(tmp_path):
         bad = dict(sd)
         bad.pop("final_conv.1.bias")
         m2.load_state_dict(bad)
+
+
+def test_synthetic_inputs_match_the_oracle_generators():
+    """bench.py's GPU arm takes its inputs from edmp_b200.synthetic, the CPU arm (oracle) from oracle.scenes /
+    oracle.weights: both arms must see bit-identical problems and weights."""
+    import torch
+    from edmp_b200 import synthetic as S
+    from oracle import sampler_oracle as so, scenes, weights
+    assert np.array_equal(S.synthetic_scene(20, 1, True, 4), scenes.synthetic_scene(20, seed=1, rotated=True, cylinders=4))
+    assert np.array_equal(S.tabletop_scene(), scenes.tabletop_scene())
+    assert np.array_equal(S.START, scenes.START) and np.array_equal(S.GOAL, scenes.GOAL)
+    _, _, abar = so.schedule()
+    assert S.alpha_bar_T() == abar[-1]
+    assert np.array_equal(S.gentle_x_T(12, abar[-1], seed=100), scenes.gentle_x_T(12, abar[-1], seed=100))
+    a, b = S.seeded_state_dict(0, final_gain=0.2), weights.seeded_state_dict(0, final_gain=0.2)
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_infer_serial_cfg_surface():
+    """The entry point's host-side plumbing: benchmark cfg -> guide tables, synthetic problem source."""
+    import infer_serial
+    from edmp_b200 import YamlConfig
+    cfg = YamlConfig(os.path.join(ROOT, "benchmark", "cfgs", "cfg_c1_synthetic.yaml"))
+    problems, scene_types = infer_serial.load_problems(cfg)
+    scene, start, goals = problems.fetch_data(0, scene_types[0])
+    assert scene.shape[1] == 10 and start.shape == (7,) and goals.shape[1] == 7
+    shipped = YamlConfig(os.path.join(ROOT, "benchmark", "cfgs", "cfg1.yaml"))     # the reference's paper config
+    assert shipped["guide"]["guides"] == [1, 2, 3, 4, 5, 10, 11, 13, 14, 16, 18, 21]
+    with pytest.raises(SystemExit):
+        infer_serial.load_problems(shipped)   # 'hybrid' needs the reference's loader + downloads
