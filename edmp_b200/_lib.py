@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libedmp_b200.so")
 PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16x3": 3, "bf16": 4, "f16x3": 5, "f16": 6}
 
 c_void_p, c_int, c_size_t, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_char_p
-c_double, c_uint64, c_longlong = ctypes.c_double, ctypes.c_uint64, ctypes.c_longlong
+c_double, c_uint64, c_longlong, c_float = ctypes.c_double, ctypes.c_uint64, ctypes.c_longlong, ctypes.c_float
 P = ctypes.POINTER
 
 # symbol -> (restype, argtypes); mirrors include/edmp_b200.h one to one
@@ -41,6 +41,10 @@ SIGNATURES = {
                                         c_int, c_void_p, c_void_p]),
     "edmp_sampler_schedule": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "edmp_sampler_last_launches": (c_longlong, [c_void_p]),
+    "edmp_sdf_scene_create": (c_int, [c_void_p, c_int, c_void_p, c_int, P(c_void_p)]),
+    "edmp_sdf_scene_destroy": (None, [c_void_p]),
+    "edmp_sdf_guide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "edmp_sdf_cloud_clearance": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

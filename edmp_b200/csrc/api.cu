@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "guide.h"
 #include "sampler.h"
+#include "sdf_guide.h"
 #include "unet.h"
 
 namespace edmp {
@@ -25,6 +26,7 @@ using namespace edmp;
 struct edmp_unet { UNet* impl; };
 struct edmp_scene { Scene* impl; };
 struct edmp_sampler { Sampler* impl; };
+struct edmp_sdf_scene { SdfScene* impl; };
 
 #define EDMP_TRY(expr)                                                     \
   try {                                                                    \
@@ -153,4 +155,28 @@ int edmp_sampler_schedule(const edmp_sampler* s, double* beta_h, double* alpha_h
 }
 long long edmp_sampler_last_launches(const edmp_sampler* s) { return s ? sampler_last_launches(s->impl) : 0; }
 
+
+/* ---- sphere / signed-distance guide family (SURVEY.md section 8 a-S) ---------------------------------- */
+int edmp_sdf_scene_create(const double* boxes_h, int n_boxes, const double* cylinders_h, int n_cylinders,
+                          edmp_sdf_scene** out) {
+  if (!out) { set_error("edmp_sdf_scene_create: null argument"); return 2; }
+  try {
+    SdfScene* s = nullptr;
+    int rc = sdf_scene_create(boxes_h, n_boxes, cylinders_h, n_cylinders, &s);
+    if (rc) return rc;
+    *out = new edmp_sdf_scene{s};
+    return 0;
+  } catch (const std::exception& e) { set_error(std::string("edmp: exception: ") + e.what()); return 3; }
+}
+void edmp_sdf_scene_destroy(edmp_sdf_scene* s) { if (s) { sdf_scene_destroy(s->impl); delete s; } }
+int edmp_sdf_guide(edmp_sdf_scene* s, const float* q_d, int n, int rows, float margin, float* cost_d, float* grad_d,
+                   float* clearance_d, void* stream) {
+  if (!s || !q_d) { set_error("edmp_sdf_guide: null argument"); return 2; }
+  EDMP_TRY(sdf_guide_launch(s->impl, q_d, n, rows, margin, cost_d, grad_d, clearance_d, (cudaStream_t)stream));
+}
+int edmp_sdf_cloud_clearance(const float* q_d, int n, int rows, const float* points_d, int n_points,
+                             float* clearance_d, void* stream) {
+  if (!q_d || !points_d || !clearance_d) { set_error("edmp_sdf_cloud_clearance: null argument"); return 2; }
+  EDMP_TRY(sdf_cloud_launch(q_d, n, rows, points_d, n_points, clearance_d, (cudaStream_t)stream));
+}
 }  // extern "C"

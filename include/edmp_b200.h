@@ -147,6 +147,27 @@ int edmp_sampler_schedule(const edmp_sampler* s, double* beta_h, double* alpha_h
 /* kernels launched by the last edmp_sample_guided[_host] call */
 long long edmp_sampler_last_launches(const edmp_sampler* s);
 
+/* ---- sphere / signed-distance guide family (SURVEY.md section 8 a-S; BASELINE.json configs[4]) ---------------
+ * Not on the reference's infer_serial.py path (its guide is the AABB-volume one above); specified by code the
+ * reference vendors: robofin/robofin/robots.py:58-174 (59 collision spheres), the URDF chain
+ * robofin/robofin/urdf/franka_panda/panda.urdf:47-235 (FK), robofin/robofin/pointcloud/torch.py:340-365
+ * (compute_spheres), mpinets/geometry.py:238-288,:456-505 (cuboid / cylinder SDF), mpinets/loss.py:88-94 (hinge).
+ * boxes_h [n_boxes,10] = (xyz, quaternion xyzw, dims) like obstacle_config; cylinders_h [n_cylinders,9] =
+ * (xyz, quaternion xyzw, radius, height); at most 64 primitives. */
+typedef struct edmp_sdf_scene edmp_sdf_scene;
+int edmp_sdf_scene_create(const double* boxes_h, int n_boxes, const double* cylinders_h, int n_cylinders,
+                          edmp_sdf_scene** out);
+void edmp_sdf_scene_destroy(edmp_sdf_scene* s);
+/* q_d float32 [rows,7,n] (n <= 64 waypoints).  cost_d [rows] = sum over (waypoint, sphere) of
+ * max(0, radius + margin - sdf(centre)); grad_d [rows,7,n] = d cost / d q (analytic); clearance_d [rows,n] =
+ * min over spheres of sdf(centre) - radius.  Any output may be null. */
+int edmp_sdf_guide(edmp_sdf_scene* s, const float* q_d, int n, int rows, float margin, float* cost_d, float* grad_d,
+                   float* clearance_d, void* stream);
+/* point-cloud variant: points_d float32 [n_points,4] (xyz + pad); clearance_d [rows,n] = min over (sphere, point) of
+ * |centre - p| - radius (n <= 50).  No reference implementation exists for this one (SURVEY.md section 8 a-S). */
+int edmp_sdf_cloud_clearance(const float* q_d, int n, int rows, const float* points_d, int n_points,
+                             float* clearance_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -399,3 +399,69 @@ def test_infer_serial_entry_point(capsys):
     assert np.isfinite(r1[0]["trajectories"]).all()
     assert np.array_equal(r1[0]["trajectories"], r2[0]["trajectories"])       # same numpy draws -> same bits
     assert "Success:" in capsys.readouterr().out
+
+
+# ------------------------------------------------------------------------------------------------
+# sphere / signed-distance guide family (SURVEY.md section 8 a-S, BASELINE config 5)
+# ------------------------------------------------------------------------------------------------
+def _sdf_trajs(rows, n, seed):
+    rng = np.random.default_rng(seed)
+    line = scenes.START[None, :, None] + (scenes.GOAL - scenes.START)[None, :, None] * np.linspace(0, 1, n)[None, None, :]
+    return line + 0.25 * rng.normal(size=(rows, 7, n))
+
+
+@pytest.mark.parametrize("case", ["general", "yaw"])
+def test_sdf_kernel_matches_reference_sdf_fixture(golden, case):
+    """Kernel clearance at a single 'sphere' cannot be probed directly, so pin the primitive SDF through the oracle:
+    oracle == reference fixture (CPU test), kernel == oracle here (cost, gradient, clearance)."""
+    from edmp_b200.lib import SphereSDFGuide
+    from oracle import sdf_oracle as sdfo
+    g = golden("sdf.npz")
+    boxes, cyls = g[case + "/boxes"], g[case + "/cylinders"]
+    guide = SphereSDFGuide(boxes, cyls, DEV, margin=0.03)
+    for rows, n in ((1, 50), (37, 48), (5, 7)):
+        q = _sdf_trajs(rows, n, seed=rows)
+        cost, grad, clr = guide.evaluate(q)
+        rc, rg, rclr = sdfo.evaluate(q, boxes, cyls, margin=0.03)
+        assert rc.max() > 0.05                                   # the scene does bite
+        np.testing.assert_allclose(cost.cpu().numpy(), rc, rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(clr.cpu().numpy(), rclr, rtol=0, atol=2e-6)
+        # the gradient is piecewise (nearest primitive, box face, hinge): compare where float32 and float64 agree on
+        # the branch, i.e. everywhere except isolated entries
+        diff = np.abs(grad.cpu().numpy() - rg)
+        assert np.mean(diff <= 1e-4 * max(1.0, np.abs(rg).max())) >= 0.995
+        assert np.median(diff) <= 1e-6
+
+
+def test_sdf_kernel_edge_cases():
+    from edmp_b200.lib import SphereSDFGuide
+    from oracle import sdf_oracle as sdfo
+    q = _sdf_trajs(3, 50, seed=2)
+    empty = SphereSDFGuide(None, None, DEV)
+    cost, grad, clr = empty.evaluate(q)
+    assert float(cost.abs().max()) == 0.0 and float(grad.abs().max()) == 0.0 and float(clr.min()) > 1e30
+    # far-away scene: no penetration, zero cost and gradient, finite positive clearance
+    far = SphereSDFGuide(np.array([[5.0, 5.0, 5.0, 0, 0, 0, 1, 0.2, 0.2, 0.2]]), None, DEV)
+    cost, grad, clr = far.evaluate(q)
+    assert float(cost.max()) == 0.0 and float(grad.abs().max()) == 0.0 and float(clr.min()) > 3.0
+    # a box swallowing the base: the fixed link0 sphere penetrates (cost) but contributes no gradient
+    base = SphereSDFGuide(np.array([[0.0, 0.0, 0.05, 0, 0, 0, 1, 0.05, 0.05, 0.05]]), None, DEV, margin=0.0)
+    q0 = np.tile(np.array([0.0, -0.5, 0.0, -2.0, 0.0, 1.6, 0.8])[None, :, None], (1, 1, 4))
+    cost, grad, clr = base.evaluate(q0)
+    rc, rg, rclr = sdfo.evaluate(q0, base.boxes, None, margin=0.0)
+    np.testing.assert_allclose(cost.cpu().numpy(), rc, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(grad.cpu().numpy(), rg, rtol=0, atol=1e-5)
+    with pytest.raises(ValueError):
+        base.evaluate(np.zeros((2, 6, 50)))
+
+
+def test_sdf_cloud_clearance_matches_oracle():
+    from edmp_b200.lib import SphereSDFGuide
+    from oracle import sdf_oracle as sdfo
+    rng = np.random.default_rng(4)
+    pts = rng.uniform([-0.3, -0.7, 0.0], [0.9, 0.7, 0.9], size=(3000, 3))      # ragged: not a multiple of the tile
+    guide = SphereSDFGuide(None, None, DEV)
+    for rows, n in ((2, 50), (9, 48)):
+        q = _sdf_trajs(rows, n, seed=10 + rows)
+        got = guide.cloud_clearance(pts, q).cpu().numpy()
+        np.testing.assert_allclose(got, sdfo.cloud_clearance(q, pts), rtol=0, atol=3e-6)

@@ -132,3 +132,47 @@ def test_sampler_oracle_end_to_end_iv(golden, sd02):
     assert np.abs(out - g["final"]).max() <= 1e-4
     best = go.choose_best_trajectory(out, scenes.START, scenes.GOAL, g["scene"])
     assert np.abs(best - g["best"]).max() <= 1e-4
+
+
+# ---- sphere / signed-distance guide family (SURVEY.md section 8 a-S) -----------------------------------------------
+@pytest.mark.parametrize("case", ["general", "yaw"])
+def test_sdf_oracle_matches_reference_geometry(golden, case):
+    """box / cylinder SDF restatement against the reference's mpinets.geometry (fixture made by make_golden_sdf)."""
+    from oracle import sdf_oracle as sdfo
+    g = golden("sdf.npz")
+    pts = torch.tensor(g[case + "/points"])
+    box = sdfo.box_sdf(pts, g[case + "/boxes"]).min(dim=-1).values.numpy()
+    cyl = sdfo.cylinder_sdf(pts, g[case + "/cylinders"]).min(dim=-1).values.numpy()
+    np.testing.assert_allclose(box, g[case + "/cuboid_sdf"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cyl, g[case + "/cylinder_sdf"], rtol=0, atol=1e-12)
+
+
+def test_sdf_oracle_fk_matches_the_dh_chain():
+    """URDF-chain FK of the sphere guide against the reference-pinned DH chain of lib/guide.py: the seven joint frames
+    (origin and all three axes) coincide, so both guide families see the same robot."""
+    from oracle import sdf_oracle as sdfo
+    q = np.random.default_rng(3).uniform(-2.5, 2.5, size=(16, 7))
+    dh = go._fk_frames64(q)
+    fk = sdfo.franka_fk(torch.tensor(q))
+    for i in range(7):
+        np.testing.assert_allclose(fk["panda_link%d" % (i + 1)].numpy(), dh[:, i], rtol=0, atol=1e-12)
+    c, r = sdfo.sphere_centres(torch.tensor(q))
+    assert c.shape == (16, 59, 3) and r.shape == (59,) and len(set(r.tolist())) == 11
+
+
+def test_sdf_oracle_gradient_is_consistent():
+    """autograd gradient of the oracle cost against central differences"""
+    from oracle import sdf_oracle as sdfo, make_golden_sdf
+    rng = np.random.default_rng(5)
+    boxes, cyls = make_golden_sdf.random_scene(rng, 6, 2)
+    q = scenes.START[None, :, None] + (scenes.GOAL - scenes.START)[None, :, None] * np.linspace(0, 1, 6)[None, None, :] \
+        + 0.1 * rng.normal(size=(2, 7, 6))
+    cost, grad, clr = sdfo.evaluate(q, boxes, cyls, margin=0.05)
+    assert cost.max() > 0 and clr.shape == (2, 6)
+    h = 1e-6
+    for (b, j, w) in [(0, 0, 1), (1, 3, 4), (0, 6, 2), (1, 1, 0)]:
+        qp, qm = q.copy(), q.copy()
+        qp[b, j, w] += h
+        qm[b, j, w] -= h
+        fd = (sdfo.evaluate(qp, boxes, cyls, 0.05, False)[0][b] - sdfo.evaluate(qm, boxes, cyls, 0.05, False)[0][b]) / (2 * h)
+        assert abs(fd - grad[b, j, w]) <= 1e-5 * max(1.0, abs(fd))
