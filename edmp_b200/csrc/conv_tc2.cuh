@@ -65,6 +65,14 @@ struct Tc2Args {
   int acc_bufs, acc_stride;       // TMEM accumulator buffers (1 or 2) and their column stride
   int half_layout;                // 1: phase-0 accumulator columns are [half][position][ct/2] (cta_group::2)
   int mma_warps;                  // 1 or 2 MMA-issuing warps (2: alternate steps, see the kernel)
+  // Row-tile chaining between consecutive conv_tc2 launches (everything a tile reads besides the weights was computed
+  // from the same trajectory rows): `done[rt]` counts this layer's finished (row tile, column tile) tiles; a tile's
+  // activation loads wait until the producing layer's counter of that row tile reaches dep_target.  With programmatic
+  // dependent launch the next layer then starts on every SM the moment that SM runs out of tiles -- no grid-wide
+  // drain between layers.  dep == null: plain griddepcontrol.wait (the producer is another kernel).
+  const int* dep;
+  int dep_target;
+  int* done;
   int b_pad;                      // 1: weight stages are [zero slot][real slots][zero slot], neighbouring stages share a zero slot
   int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
   int ct_log2, cg_log2, nct_log2; // ct, cg and n_col_tiles are powers of two
@@ -121,7 +129,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!umma::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 // Mish = x * n / (n + 2), n = e^x (e^x + 2), with the single-instruction ex2 / rcp approximations (relative error
@@ -132,6 +140,12 @@ __device__ __forceinline__ float mish(float x) {
   const float n = e * (e + 2.0f);
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.0f));
   return x * (n * r);
+}
+// acquire-load of a global progress counter
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 // non-blocking phase test
 __device__ __forceinline__ bool test(uint64_t* bar, uint32_t parity) {
@@ -224,7 +238,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   if (CG == 2) t2::cluster_sync_all();
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  pdl_wait();   // everything above overlapped the previous kernel; activations are read below
+  // everything above overlapped the previous kernel; activations are read below.  Chained layers synchronise per row
+  // tile instead (the producer thread, before a tile's first activation load)
+  if (a.dep == nullptr) pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -235,10 +251,32 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       int ta = unit0, pa = 0, cca = 0, lia = 0;     // activation stream position (tile, phase, chunk, input position)
       int tb = unit0, pb = 0, ccb = 0;              // weight stream position
+      int ta_ready = -1;                            // tile whose row-tile dependency has been observed
+      long long dep_t0 = 0;
       // skip leading unused positions
       while (ta < n_tiles && a.ph[pa].sched[lia].n_slots == 0) ++lia;
       while (ta < n_tiles || tb < n_tiles) {
-        if (ta < n_tiles && t2::test(a_empty + as, aph ^ 1)) {
+        bool a_go = ta < n_tiles && t2::test(a_empty + as, aph ^ 1);
+        if (a_go && a.dep != nullptr && ta != ta_ready) {
+          // first activation load of this tile: the producing layer must have finished this row tile (the weight
+          // stream below keeps being served meanwhile)
+          const int rt_dep = (ta >> a.nct_log2) * CG + (int)rank;
+          // (a pair's padding row tile past the batch has no producer: its operand blocks are the zero-filled tail)
+          if (rt_dep * kTcRows < a.rows && t2::ld_acquire(a.dep + rt_dep) < a.dep_target) {
+            a_go = false;
+            if (dep_t0 == 0) dep_t0 = clock64();
+            else if (clock64() - dep_t0 > (1ll << 32)) {   // ~2 s: a protocol bug traps instead of hanging the GPU
+              printf("edmp: conv_tc2 row-tile dependency timed out (block %d, row tile %d: %d of %d)\n", blockIdx.x, rt_dep,
+                     t2::ld_acquire(a.dep + rt_dep), a.dep_target);
+              __trap();
+            }
+          } else {
+            dep_t0 = 0;
+            asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (bulk copy) reads
+            ta_ready = ta;
+          }
+        }
+        if (a_go) {
           const Tc2Phase& ph = a.ph[pa];
           const int ka = ph.a.C >> E::kShift, kb = ph.b.C >> E::kShift;
           const bool first = cca < ka;
@@ -684,6 +722,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         umma::tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + buf, 0); else umma::mbar_arrive(acc_empty + buf); }
+      }
+      if (a.done != nullptr) {
+        // publish the tile: every thread's stores are fenced to GPU scope, then one thread bumps the row tile's counter
+        __threadfence();
+        t2::bar_epilogue();
+        if (et == 0) atomicAdd(a.done + rt, 1);
       }
       if (dbg) { const long long te = clock64(); t_busy += te - t_start; t_fin += te - tf0; }
       if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) fph ^= 1; } else { fph ^= 1; }

@@ -234,6 +234,9 @@ struct UNet {
   bool final_fused = false;   // final 1x1 conv fused into the last position-major layer
   bool tc2 = false;           // persistent second-generation kernel (conv_tc2.cuh) for the rows-as-M levels
   bool cg2 = false;           // CTA pairs (cta_group::2) for the horizon 2 / 4 levels (large batches)
+  bool chain = false;         // row-tile chaining between consecutive conv_tc2 launches (conv_tc2.cuh)
+  int* tile_done = nullptr;   // [layer][row tile] progress counters, zeroed at the start of every forward
+  int tile_stride = 0;        // row tiles per layer in tile_done
   int sm_count = 148;
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
@@ -1142,6 +1145,24 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
     u->final_b = b.vec("final_conv.1.bias", kDof);
   }
 
+  // progress counters of the chained conv_tc2 launches
+  u->chain = u->tc2 && pdl_enabled() && getenv("EDMP_NO_CHAIN") == nullptr;
+  u->tile_stride = ((max_rows + kTcRows - 1) / kTcRows + 1) & ~1;
+  if (u->chain) {
+    const size_t bytes = u->layers.size() * (size_t)u->tile_stride * sizeof(int);
+    b.ok = b.ok && cudaMalloc(&u->tile_done, bytes) == cudaSuccess;
+    if (b.ok) { u->dev_allocs.push_back(u->tile_done); cudaMemset(u->tile_done, 0, bytes); }
+    for (size_t i = 0; i < u->layers.size() && b.ok; ++i) {
+      Layer& ly = u->layers[i];
+      if (ly.kind != LAYER_TC2) continue;
+      ly.t2.done = u->tile_done + i * (size_t)u->tile_stride;
+      if (i > 0 && u->layers[i - 1].kind == LAYER_TC2) {
+        ly.t2.dep = u->tile_done + (i - 1) * (size_t)u->tile_stride;
+        ly.t2.dep_target = u->layers[i - 1].t2.n_col_tiles;
+      }
+    }
+  }
+
   // time-embedding table: TimeEmbedding (blocks.py:76-92) then each block's TimeMLP (:58-72)
   u->temb_width = b.temb_width;
   std::vector<float> table((size_t)kTSteps * b.temb_width);
@@ -1250,6 +1271,7 @@ int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStrea
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
+  if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
   for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, eps, st);
   if (!u->final_fused) {
     const int threads = 128;
@@ -1275,6 +1297,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
   std::vector<double> acc(n, 0.0);
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
   for (int it = 0; it < iters; ++it) {
+    if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
     EDMP_CK(cudaEventRecord(ev[0], st));
     for (int i = 0; i < nl; ++i) {
       run_layer(u, u->layers[i], x, temb_row, rows, eps, st);
