@@ -81,7 +81,6 @@ struct Tc2Args {
   void *out_hi, *out_lo;          // tiled output (or position-major images when out_pm)
   int out_pm;
   long long* dbg;                 // optional [ctas][16] clock64 stamps / counters, normally null
-  int dbg_skip;                   // profiling experiments only (EDMP_T2_SKIP): 1 no stores, 2 no Mish, 4 no residual loads, 8 no combine
 };
 
 namespace t2 {
@@ -618,7 +617,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             unit_pos(u << 4, lo, c0);
             t2::tmem_ld16_nowait(t_acc + (uint32_t)(a.ph[0].d_col + (u << 4)), yr[j]);
             if (a.mode == TC_GN_RES_PW) t2::tmem_ld16_nowait(t_acc + (uint32_t)(a.ph[1].d_col + lo * ct + c0), rr[j]);
-            if (a.mode == TC_GN_RES_ID && !(a.dbg_skip & 4)) {
+            if (a.mode == TC_GN_RES_ID) {
               // out + x (blocks.py:164, identity residual): x = hi + lo of the tiled block input
               const int kr = lo * a.res.C + nt * ct + c0;
               const size_t rsrc = ((size_t)rt * (L * (a.res.C >> E::kShift)) + (kr >> E::kShift)) * kTcBlockBytes;
@@ -639,7 +638,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           mean[j][0] = mean[j][1] = 0.0f;
           rstd[j][0] = rstd[j][1] = 1.0f;
           const int u = part + 4 * (kb + j);
-          if (a.mode != TC_BIAS && u < n_units && !(a.dbg_skip & 8)) {
+          if (a.mode != TC_BIAS && u < n_units) {
             int lo, c0;
             unit_pos(u << 4, lo, c0);
             const int g = two ? (c0 >> 3) : (c0 >> cg_log2);
@@ -676,7 +675,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { const float z = (v[e] - m_) * (r_ * ga[e]) + be[e]; v[e] = ((a.dbg_skip & 2) ? z : t2::mish(z)) + te[e]; }
+                for (int e = 0; e < 8; ++e) v[e] = t2::mish((v[e] - m_) * (r_ * ga[e]) + be[e]) + te[e];
               }
               if (a.mode == TC_GN_RES_PW) {
                 const float* pb = s_par + 512 + c0 + m * 8;
@@ -700,7 +699,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 const float2 hf = unpack16x2<EL>(hh[e]);
                 ll[e] = pack16x2<EL>(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
               }
-              if (grow < a.rows && !(a.dbg_skip & 1)) {
+              if (grow < a.rows) {
                 size_t dst;
                 if (a.out_pm) {
                   // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]

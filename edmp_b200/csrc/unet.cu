@@ -1235,7 +1235,6 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
     a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
-    { static const int skip = getenv("EDMP_T2_SKIP") ? atoi(getenv("EDMP_T2_SKIP")) : 0; a.dbg_skip = skip; }
     if (ly.cta_group == 2) {
       a.n_row_tiles = (a.n_row_tiles + 1) & ~1;
       const int n_pair_tiles = (a.n_row_tiles / 2) * a.n_col_tiles;
