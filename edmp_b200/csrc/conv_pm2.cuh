@@ -1,0 +1,329 @@
+// Persistent position-major tensor-core kernel for the horizon 25 / 50 levels: second generation of conv_pm.cuh
+// (same GEMM view -- M lanes = (position, row) of a block of 8 trajectory rows, a filter tap = a descriptor start
+// offset -- and the same operand images and epilogue arithmetic).
+//
+// conv_pm_kernel is latency-bound: a CTA loads its operands (~3k cycles), issues its MMAs (~5-10k), waits for them and
+// then runs a ~20k-cycle epilogue whose warps sit idle before that; with two CTAs per SM only ~1 epilogue is active on
+// an SM at any time and its issue slots are 14 % used (profiles/r1_f16x3_8190rows_cta_phases_v3.txt, ncu source
+// counters).  Here ONE CTA per SM stays resident and walks row blocks:
+//   * the layer's weights (all output channels: the MMA's N is the layer's C_out, 32 or 64) are loaded once per CTA;
+//   * the activation image of block k+1 is fetched as soon as the MMAs of block k have read theirs;
+//   * two TMEM accumulator buffers and TWO epilogue groups (8 warps each, blocks alternate between them): two
+//     epilogues are always in flight next to the load + MMA of the following block.
+// Reference ops covered: as conv_pm.cuh (Conv1dBlock blocks.py:13-34, ResidualConvolutionBlock :137-166, the stride-2
+// Conv1d :211, ConvTranspose1d :249, final_conv temporalunet.py:35-36).
+#pragma once
+#include "conv_pm.cuh"
+
+namespace edmp {
+
+constexpr int kPm2Groups = 2;
+constexpr int kPm2Threads = 64 + kPm2Groups * kPmEpiThreads;   // producer, MMA, 2 x 8 epilogue warps = 576
+
+__device__ __forceinline__ void pm2_group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kPmEpiThreads) : "memory"); }
+
+// CG = channels per GroupNorm group (4: C_out = 32, 8: C_out = 64); the CTA computes all C_out = 8 * CG channels.
+template <int EL, int CG>
+__global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_constant__ PmArgs a) {
+  static_assert(EL != TC_EL_TF32, "position-major kernels use 16-bit operand elements");
+  constexpr int COUT = 8 * CG;
+  constexpr int UNITS = COUT / 16;            // 16-column accumulator units per M tile
+  constexpr int NG = 8;                       // GroupNorm groups
+  constexpr int GPU_ = 16 / CG;               // groups per unit (4 or 2)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_w, bar_a_full, bar_a_empty, bar_acc_full[kPm2Groups], bar_acc_empty[kPm2Groups];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_par[5 * 64];       // bias | gamma | beta | temb | aux bias
+  __shared__ float s_fw[7 * 64 + 8];                  // final 1x1 conv weights + bias
+  __shared__ float s_red[kPm2Groups][kPmEpiWarps][8][8];   // [group][warp][row][gn group] partial sums
+  __shared__ float s_mr[kPm2Groups][2][8][8];              // [group][mean | rstd][row][gn group]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.a.C;
+  const int rby = 2 * C;                      // bytes per (position, row) line
+  const int atom = 8 * rby;
+  const int nkc = a.b.C ? 2 : 1;
+  const int nparts = a.split ? 2 : 1;
+  const int ntiles = (a.n_m + 15) >> 4;
+  const int n_blocks = (a.rows + kPmRows - 1) / kPmRows;
+  const int acc_cols = (a.n_groups + a.aux) * ntiles * COUT;     // accumulator columns of one block (<= 256)
+  uint8_t* a_smem = smem;                                        // [part][source] images
+  uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][COUT rows][rby]
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&bar_w, 1);
+    umma::mbar_init(&bar_a_full, 1);
+    umma::mbar_init(&bar_a_empty, 1);
+    for (int g = 0; g < kPm2Groups; ++g) { umma::mbar_init(bar_acc_full + g, 1); umma::mbar_init(bar_acc_empty + g, kPmEpiWarps); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(&tmem_slot);
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;
+    if (e < COUT) {
+      s_par[e] = a.bias ? a.bias[e] : 0.0f;
+      s_par[64 + e] = a.gamma ? a.gamma[e] : 1.0f;
+      s_par[128 + e] = a.beta ? a.beta[e] : 0.0f;
+      s_par[192 + e] = a.temb ? a.temb[e] : 0.0f;
+      s_par[256 + e] = a.aux_bias ? a.aux_bias[e] : 0.0f;
+    }
+    if (a.eps) {
+      for (int i = e; i < 7 * COUT + 7; i += kPm2Groups * kPmEpiThreads) s_fw[i] = i < 7 * COUT ? a.fw[i] : a.fb[i - 7 * COUT];
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: weights once (they do not depend on the previous kernel), then one activation image per block =====
+    if (lane == 0) {
+      umma::mbar_arrive_expect_tx(&bar_w, (uint32_t)(nparts * a.w_bytes_part));
+      for (int p = 0; p < nparts; ++p)
+        umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, (const uint8_t*)(p ? a.w_lo : a.w_hi), (uint32_t)a.w_bytes_part, &bar_w);
+      pdl_wait();   // activations of the previous kernel are read below
+      uint32_t ph = 0;
+      for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+        umma::mbar_wait(&bar_a_empty, ph ^ 1);     // the MMAs of the previous block have read the image
+        umma::mbar_arrive_expect_tx(&bar_a_full, (uint32_t)(nparts * nkc * a.a_bytes_img));
+        for (int p = 0; p < nparts; ++p)
+          for (int s = 0; s < nkc; ++s) {
+            const PmAct& src = s ? a.b : a.a;
+            const uint8_t* g = (const uint8_t*)(p ? src.lo : src.hi) + (size_t)rb * a.a_bytes_img;
+            umma::bulk_g2s(a_smem + (size_t)(p * nkc + s) * a.a_bytes_img, g, (uint32_t)a.a_bytes_img, &bar_a_full);
+          }
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
+    umma::mbar_wait(&bar_w, 0);
+    const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
+    const uint32_t a_lo_off = (uint32_t)(nkc * a.a_bytes_img), w_lo_off = (uint32_t)a.w_bytes_part;
+    const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
+    const int ksteps = C >> 4;
+    uint32_t ph = 0, k = 0;
+    for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x, ++k) {
+      const uint32_t g = k & 1, use = k >> 1;
+      umma::mbar_wait(bar_acc_empty + g, (use & 1) ^ 1);      // the group has drained this accumulator buffer
+      umma::mbar_wait(&bar_a_full, ph);
+      ph ^= 1;
+      umma::tc_fence_after();
+      const uint32_t acc0 = tmem_base + g * 256u;
+      for (int mt = 0; mt < ntiles; ++mt) {
+        uint32_t touched = 0;
+        for (int ti = 0; ti < a.n_terms; ++ti) {
+          const PmTerm t = a.terms[ti];
+          const uint32_t d = acc0 + (uint32_t)((t.acc * ntiles + mt) * COUT);
+          for (int kc = 0; kc < nkc; ++kc) {
+            const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
+            const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
+            const uint64_t da_hi = pm_desc(a_addr, a.stride * atom, rby), da_lo = pm_desc(a_addr + a_lo_off, a.stride * atom, rby);
+            const uint64_t db_hi = pm_desc(w_addr, atom, rby), db_lo = pm_desc(w_addr + w_lo_off, atom, rby);
+            const uint32_t acc_first = (touched >> t.acc) & 1u;
+            if (umma::elect_one()) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t acc = acc_first | (uint32_t)(ks > 0);
+                if (a.split) {
+                  umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                  umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                  umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                } else {
+                  umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                }
+              }
+            }
+            __syncwarp();
+            touched |= 1u << t.acc;
+          }
+        }
+      }
+      if (umma::elect_one()) {
+        umma::mma_commit(&bar_a_empty);          // the image may be overwritten once these MMAs have read it
+        umma::mma_commit(bar_acc_full + g);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: two groups of 8 warps, blocks alternate between them =====
+    const int grp = (warp - 2) >> 3;
+    const int ew = (warp - 2) & 7;
+    const int et = threadIdx.x - 64 - grp * kPmEpiThreads;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access (warp id mod 4)
+    const int half = ew >> 2;                   // which M tiles (mt & 1 == half)
+    const int row = lane & 7;
+    const int pos_in_tile = quarter * 4 + (lane >> 3);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 256u;
+    float (*red)[8][8] = s_red[grp];
+    float (*mr)[8][8] = s_mr[grp];
+    (void)acc_cols;
+    uint32_t k = (uint32_t)grp;
+    for (int rb = blockIdx.x + grp * gridDim.x; rb < n_blocks; rb += kPm2Groups * gridDim.x, k += kPm2Groups) {
+      const uint32_t use = k >> 1;
+      const int grow = rb * kPmRows + row;        // global trajectory row
+      umma::mbar_wait(bar_acc_full + grp, use & 1);
+      __syncwarp();
+      umma::tc_fence_after();
+
+      if (a.mode != PM_BIAS) {
+        // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26), two-pass
+        const float inv_n = 1.0f / (float)(CG * a.n_m);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          float s[NG];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) s[g] = 0.0f;
+          for (int mt = half; mt < ntiles; mt += 2) {
+            const bool valid = (16 * mt + pos_in_tile) < a.n_m;
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+              float v[16], b[16];
+              umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT + u * 16), v);
+              pm_ld_par16(s_par + u * 16, b);
+              if (valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int g = u * GPU_ + i / CG;
+                  const float y = fmaf(v[i], a.acc_scale, b[i]);
+                  if (pass == 0) s[g] += y;
+                  else { const float d = y - mr[0][row][g]; s[g] = fmaf(d, d, s[g]); }
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            s[g] += __shfl_xor_sync(0xffffffffu, s[g], 8);
+            s[g] += __shfl_xor_sync(0xffffffffu, s[g], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) red[ew][row][g] = s[g];
+          }
+          pm2_group_barrier(grp);
+          if (et < 8 * NG) {
+            const int r = et / NG, g = et % NG;
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kPmEpiWarps; ++w) t += red[w][r][g];
+            mr[pass][r][g] = pass == 0 ? t * inv_n : rsqrtf(t * inv_n + 1e-5f);
+          }
+          pm2_group_barrier(grp);
+        }
+      }
+
+      const int n_acc = a.n_groups + a.aux;
+      const int rby_o = 2 * a.cout;               // output line bytes
+      for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
+        const bool is_aux = a.aux && g_acc == a.n_groups;
+        const bool gn = !is_aux && a.mode != PM_BIAS;
+        const float sc = is_aux ? a.aux_scale : a.acc_scale;
+        const float* pb = is_aux ? s_par + 256 : s_par;
+        void* o_hi = is_aux ? a.aux_hi : a.out_hi;
+        void* o_lo = is_aux ? a.aux_lo : a.out_lo;
+        for (int mt = half; mt < ntiles; mt += 2) {
+          const int idx = 16 * mt + pos_in_tile;
+          const bool valid = idx < a.n_m && grow < a.rows;
+          const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
+          const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
+          float fin[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) fin[j] = 0.0f;
+#pragma unroll
+          for (int u = 0; u < UNITS; ++u) {
+            float v[16];
+            umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT + u * 16), v);
+            // identity residual (blocks.py:164): issue the loads before the arithmetic that hides their latency
+            uint4 rh[2], rl[2];
+            const bool res = valid && !is_aux && a.mode == PM_GN_RES;
+            if (res) {
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
+                rh[m] = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+                rl[m] = a.res.lo ? *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off) : make_uint4(0, 0, 0, 0);
+              }
+            }
+            {
+              float b[16];
+              pm_ld_par16(pb + u * 16, b);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc, b[i]);
+            }
+            if (gn) {
+              float ga[16], be[16], te[16];
+              pm_ld_par16(s_par + 64 + u * 16, ga);
+              pm_ld_par16(s_par + 128 + u * 16, be);
+              pm_ld_par16(s_par + 192 + u * 16, te);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int g = u * GPU_ + i / CG;
+                const float t = (v[i] - mr[0][row][g]) * mr[1][row][g] * ga[i] + be[i];
+                v[i] = pm_mish(t) + te[i];
+              }
+            }
+            if (!valid) continue;
+            if (res) {
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                float x[8];
+                tc_chunk_sum<EL>(rh[m], rl[m], a.res.lo != nullptr, x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[m * 8 + e] += x[e];
+              }
+            }
+            if (o_hi || (!is_aux && a.tc_hi)) {
+              uint4 h[4], l[4];
+              tc_split_store<EL>(v, (is_aux ? a.aux_lo : (a.tc_hi ? a.tc_lo : a.out_lo)) != nullptr, h, l);
+              if (o_hi) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
+                  *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
+                  if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
+                }
+              } else {
+                // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
+                const int rt = grow / kTcRows, rl_ = grow % kTcRows;
+                const int kk = lo * a.cout + u * 16;
+                const size_t blk = ((size_t)rt * (a.lout * (a.cout >> 6)) + (kk >> 6)) * kTcBlockBytes;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  const size_t off = blk + tc_swz_bytes(rl_, ((kk & 63) >> 3) + m);
+                  *reinterpret_cast<uint4*>((uint8_t*)a.tc_hi + off) = h[m];
+                  if (a.tc_lo) *reinterpret_cast<uint4*>((uint8_t*)a.tc_lo + off) = l[m];
+                }
+              }
+            }
+            if (!is_aux && a.eps) {
+              // fused final nn.Conv1d(32, 7, 1) (temporalunet.py:36): partial sums over this unit's channels
+#pragma unroll
+              for (int j = 0; j < 7; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) fin[j] = fmaf(s_fw[j * COUT + u * 16 + i], v[i], fin[j]);
+            }
+          }
+          if (valid && !is_aux && a.eps) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) a.eps[((size_t)grow * 7 + j) * a.lout + lo] = fin[j] + s_fw[7 * COUT + j];
+          }
+        }
+      }
+      // every accumulator read of this block is complete: hand the buffer back to the MMA warp
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(bar_acc_empty + grp);
+    }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace edmp

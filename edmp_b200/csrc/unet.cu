@@ -21,6 +21,7 @@
 #include "conv_tc.cuh"
 #include "conv_pm.cuh"
 #include "conv_tc2.cuh"
+#include "conv_pm2.cuh"
 #include "edmp_b200.h"
 
 namespace edmp {
@@ -234,6 +235,7 @@ struct UNet {
   bool final_fused = false;   // final 1x1 conv fused into the last position-major layer
   bool tc2 = false;           // persistent second-generation kernel (conv_tc2.cuh) for the rows-as-M levels
   bool cg2 = false;           // CTA pairs (cta_group::2) for the horizon 2 / 4 levels (large batches)
+  bool pm2 = false;           // persistent position-major kernel (conv_pm2.cuh): one CTA per SM, all output channels per CTA
   bool chain = false;         // row-tile chaining between consecutive conv_tc2 launches (conv_tc2.cuh)
   int* tile_done = nullptr;   // [layer][row tile] progress counters, zeroed at the start of every forward
   int tile_stride = 0;        // row tiles per layer in tile_done
@@ -809,8 +811,9 @@ struct Builder {
             const float w = scale * wfn(co, kc * C + c, sl);
             const int r8 = co & 7, chunk = (c * 2) >> 4;
             const int sw = rby == 128 ? (chunk ^ r8) : (rby == 64 ? (chunk ^ ((r8 >> 1) & 3)) : (chunk ^ ((r8 >> 2) & 1)));
-            const int nh = co / kPmCt, cl = co % kPmCt;
-            const size_t off = ((size_t)((nh * total_slots + slot0 + sl) * nkc + kc) * kPmCt + cl) * rby + (size_t)(sw << 4) +
+            const int pct = u->pm2 ? cout : kPmCt;   // output channels per weight image (per CTA)
+            const int nh = co / pct, cl = co % pct;
+            const size_t off = ((size_t)((nh * total_slots + slot0 + sl) * nkc + kc) * pct + cl) * rby + (size_t)(sw << 4) +
                                ((c * 2) & 15);
             uint16_t h, l;
             encode16(w, &h, &l);
@@ -828,18 +831,19 @@ struct Builder {
     t.a_bytes_img = (t.lin + 4) * atom;
     const int nimg = nkc * nparts;
     t.a_bytes_total = nimg * t.a_bytes_img;
-    t.w_bytes_part = n_slots * nkc * kPmCt * rby;   // per 32-channel column tile
+    const int pct = u->pm2 ? t.cout : kPmCt;        // output channels per CTA
+    t.w_bytes_part = n_slots * nkc * pct * rby;     // per column tile
     // the last M tile reads (finite garbage) past the last image: that tail may overlap the weights
     const size_t tail_end = (size_t)(nimg - 1) * t.a_bytes_img + (size_t)atoms_needed * atom;
     const int ntiles = (t.n_m + 15) / 16;
-    int cols = (t.n_groups + t.aux) * ntiles * kPmCt, p2 = 32;
+    int cols = (t.n_groups + t.aux) * ntiles * pct, p2 = 32;
     while (p2 < cols) p2 *= 2;
     t.tmem_cols = p2;
-    ok = ok && p2 <= 512;
+    ok = ok && p2 <= (u->pm2 ? 256 : 512);   // (persistent kernel: two accumulator buffers of 256 columns)
     ly.kind = LAYER_PM;
     ly.tc_smem = 1024 + std::max((((size_t)t.a_bytes_total + 1023) & ~(size_t)1023) + (size_t)nparts * t.w_bytes_part,
                                  tail_end) + 256;
-    ok = ok && ly.tc_smem <= 232448 - 6144 - 1024;
+    ok = ok && ly.tc_smem <= 232448 - (u->pm2 ? 10240 : 6144) - 1024;
   }
 
   // Conv1dBlock (conv5 + GroupNorm + Mish [+ time embedding] [+ identity residual]) on the
@@ -1056,6 +1060,10 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -1076,6 +1084,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   // kernel when the operand elements are 16-bit, else on the CUDA-core kernels.
   u->pm = u->tc && u->tc_16() && getenv("EDMP_NO_PM") == nullptr;
   u->tc2 = u->pm && getenv("EDMP_TC_V1") == nullptr;
+  u->pm2 = u->pm && getenv("EDMP_PM_V1") == nullptr;
   // pairs halve the number of schedulable tiles: only worth it when the batch still fills the machine
   u->cg2 = u->tc2 && getenv("EDMP_NO_CG2") == nullptr && (max_rows >= 4096 || getenv("EDMP_CG2") != nullptr);
   {
@@ -1214,6 +1223,13 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     if (ly.pm_final) a.eps = eps;
     a.dbg = u->dbg;
+    if (u->pm2) {
+      dim3 grid2(std::min((rows + kPmRows - 1) / kPmRows, u->sm_count));
+      auto k2 = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm2_kernel<TC_EL_F16, 4> : conv_pm2_kernel<TC_EL_F16, 8>)
+                                      : (a.cout == 32 ? conv_pm2_kernel<TC_EL_BF16, 4> : conv_pm2_kernel<TC_EL_BF16, 8>);
+      launch_pdl(k2, grid2, dim3(kPm2Threads), ly.tc_smem, st, a);
+      return;
+    }
     dim3 grid((rows + kPmRows - 1) / kPmRows, a.cout / kPmCt);
     auto k = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm_kernel<TC_EL_F16, 4> : conv_pm_kernel<TC_EL_F16, 8>)
                                    : (a.cout == 32 ? conv_pm_kernel<TC_EL_BF16, 4> : conv_pm_kernel<TC_EL_BF16, 8>);
@@ -1363,7 +1379,7 @@ const char* unet_op_kernel(const UNet* u, int i) {
   switch (ly.kind) {
     case LAYER_TC2: return ly.cta_group == 2 ? "conv_tc2_pair" : "conv_tc2";
     case LAYER_TC: return "conv_tc";
-    case LAYER_PM: return "conv_pm";
+    case LAYER_PM: return u->pm2 ? "conv_pm2" : "conv_pm";
     case LAYER_SIMT: return "conv_simt";
     default: return "pack";
   }

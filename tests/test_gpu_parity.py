@@ -131,6 +131,19 @@ def test_unet_headline_batch_matches_small_batch(tmp_path_factory, sd):
         assert torch.isfinite(full).all()
 
 
+def test_unet_headline_batch_is_deterministic(tmp_path_factory, sd):
+    """Soak for the asynchronous machinery of the persistent kernels (row-tile chaining across launches, two
+    MMA-issuing warps, CTA pairs): 25 forwards of the same 8190-row batch at different time steps interleaved must
+    reproduce bit for bit; a missed dependency would show as a mismatch."""
+    m = _model(tmp_path_factory, sd, "f16x3")
+    x = torch.randn(8190, 7, 50, generator=torch.Generator().manual_seed(21)).to(DEV) * 1.5
+    ref = {t: m(x, t).clone() for t in (255, 77, 1)}
+    for k in range(25):
+        t = (255, 77, 1)[k % 3]
+        assert torch.equal(m(x, t), ref[t]), "forward %d (t=%d) differs" % (k, t)
+    torch.cuda.synchronize()
+
+
 def test_unet_rejects_bad_arguments(model):
     from edmp_b200 import _lib
     with pytest.raises(ValueError):
