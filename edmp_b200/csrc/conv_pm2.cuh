@@ -20,6 +20,15 @@ namespace edmp {
 constexpr int kPm2Groups = 2;
 constexpr int kPm2Threads = 64 + kPm2Groups * kPmEpiThreads;   // producer, MMA, 2 x 8 epilogue warps = 576
 
+// One precomputed MMA step: the shared-memory addresses and the TMEM offset do not depend on the row block, so the
+// whole issue schedule of a block is tabulated once per CTA; the issuing warp then only streams table entries (the
+// descriptor arithmetic of conv_pm_kernel's loop cost ~100 cycles per MMA against the 40-cycle issue floor).
+struct __align__(16) PmIssue {   // low words of the four UMMA descriptors (the high words are per-kernel constants)
+  uint32_t da_hi, da_lo, db_hi, db_lo;
+  uint32_t d_off, acc, pad0, pad1;
+};
+constexpr int kPm2MaxIssue = 128;
+
 __device__ __forceinline__ void pm2_group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kPmEpiThreads) : "memory"); }
 
 // CG = channels per GroupNorm group (4: C_out = 32, 8: C_out = 64); the CTA computes all C_out = 8 * CG channels.
@@ -38,6 +47,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   __shared__ float s_fw[7 * 64 + 8];                  // final 1x1 conv weights + bias
   __shared__ float s_red[kPm2Groups][kPmEpiWarps][8][8];   // [group][warp][row][gn group] partial sums
   __shared__ float s_mr[kPm2Groups][2][8][8];              // [group][mean | rstd][row][gn group]
+  __shared__ PmIssue s_issue[kPm2MaxIssue];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = a.a.C;
@@ -51,6 +61,8 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   uint8_t* a_smem = smem;                                        // [part][source] images
   uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][COUT rows][rby]
 
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     umma::mbar_init(&bar_w, 1);
@@ -59,7 +71,30 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     for (int g = 0; g < kPm2Groups; ++g) { umma::mbar_init(bar_acc_full + g, 1); umma::mbar_init(bar_acc_empty + g, kPmEpiWarps); }
     umma::fence_barrier_init();
   }
-  if (warp == 1) umma::tmem_alloc<512>(&tmem_slot);
+  if (warp == 1) {
+    umma::tmem_alloc<512>(&tmem_slot);
+    // issue table: entry e = (M tile, term, K chunk, 32-byte K step)
+    const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
+    const int ksteps = C >> 4;
+    const int n_issue = ntiles * a.n_terms * nkc * ksteps;
+    for (int e = lane; e < n_issue; e += 32) {
+      const int ks = e % ksteps, kc = (e / ksteps) % nkc, ti = (e / (ksteps * nkc)) % a.n_terms, mt = e / (ksteps * nkc * a.n_terms);
+      const PmTerm t = a.terms[ti];
+      uint32_t seen = 0;
+      for (int tj = 0; tj < ti; ++tj) seen |= (a.terms[tj].acc == t.acc) ? 1u : 0u;
+      const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
+      const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
+      PmIssue it;
+      it.da_hi = (uint32_t)(pm_desc(a_addr, a.stride * atom, rby) + 2 * ks);
+      it.da_lo = (uint32_t)(pm_desc(a_addr + (uint32_t)(nkc * a.a_bytes_img), a.stride * atom, rby) + 2 * ks);
+      it.db_hi = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);
+      it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)a.w_bytes_part, atom, rby) + 2 * ks);
+      it.d_off = (uint32_t)((t.acc * ntiles + mt) * COUT);
+      it.acc = (seen | (uint32_t)(kc > 0) | (uint32_t)(ks > 0)) ? 1u : 0u;
+      it.pad0 = it.pad1 = 0;
+      s_issue[e] = it;
+    }
+  }
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
     if (e < COUT) {
@@ -101,45 +136,37 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
     umma::mbar_wait(&bar_w, 0);
-    const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
-    const uint32_t a_lo_off = (uint32_t)(nkc * a.a_bytes_img), w_lo_off = (uint32_t)a.w_bytes_part;
     const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
-    const int ksteps = C >> 4;
+    const int n_issue = ntiles * a.n_terms * nkc * (C >> 4);
+    const uint64_t hi_a = pm_desc(0, a.stride * atom, rby) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
+    const uint64_t hi_b = pm_desc(0, atom, rby) & 0xFFFFFFFF00000000ull;
     uint32_t ph = 0, k = 0;
+    long long w_acc = 0, w_a = 0, t_begin = dbg ? clock64() : 0;
     for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x, ++k) {
       const uint32_t g = k & 1, use = k >> 1;
+      long long tw = dbg ? clock64() : 0;
       umma::mbar_wait(bar_acc_empty + g, (use & 1) ^ 1);      // the group has drained this accumulator buffer
+      if (dbg) { const long long t1 = clock64(); w_acc += t1 - tw; tw = t1; }
       umma::mbar_wait(&bar_a_full, ph);
+      if (dbg) w_a += clock64() - tw;
       ph ^= 1;
       umma::tc_fence_after();
       const uint32_t acc0 = tmem_base + g * 256u;
-      for (int mt = 0; mt < ntiles; ++mt) {
-        uint32_t touched = 0;
-        for (int ti = 0; ti < a.n_terms; ++ti) {
-          const PmTerm t = a.terms[ti];
-          const uint32_t d = acc0 + (uint32_t)((t.acc * ntiles + mt) * COUT);
-          for (int kc = 0; kc < nkc; ++kc) {
-            const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
-            const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
-            const uint64_t da_hi = pm_desc(a_addr, a.stride * atom, rby), da_lo = pm_desc(a_addr + a_lo_off, a.stride * atom, rby);
-            const uint64_t db_hi = pm_desc(w_addr, atom, rby), db_lo = pm_desc(w_addr + w_lo_off, atom, rby);
-            const uint32_t acc_first = (touched >> t.acc) & 1u;
-            if (umma::elect_one()) {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t acc = acc_first | (uint32_t)(ks > 0);
-                if (a.split) {
-                  umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                  umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                  umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
-                } else {
-                  umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                }
-              }
-            }
-            __syncwarp();
-            touched |= 1u << t.acc;
+      PmIssue cur = s_issue[0];
+      for (int e = 0; e < n_issue; ++e) {
+        const PmIssue nxt = s_issue[e + 1 < n_issue ? e + 1 : e];   // prefetch: the issue below blocks for ~40 cycles per MMA
+        const uint32_t d = acc0 + cur.d_off;
+        if (umma::elect_one()) {
+          if (a.split) {
+            umma::mma_bf16(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
+            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
+            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, 1u);
+          } else {
+            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, cur.acc);
           }
         }
+        __syncwarp();
+        cur = nxt;
       }
       if (umma::elect_one()) {
         umma::mma_commit(&bar_a_empty);          // the image may be overwritten once these MMAs have read it
@@ -147,6 +174,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       }
       __syncwarp();
     }
+    if (dbg && lane == 0) { dbg[2] = w_acc; dbg[3] = 0; dbg[4] = w_a; dbg[5] = clock64() - t_begin; }
   } else {
     // ===== epilogue: two groups of 8 warps, blocks alternate between them =====
     const int grp = (warp - 2) >> 3;
@@ -161,12 +189,16 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     float (*mr)[8][8] = s_mr[grp];
     (void)acc_cols;
     uint32_t k = (uint32_t)grp;
+    long long w_full = 0, t_busy = 0, t_stats = 0;
     for (int rb = blockIdx.x + grp * gridDim.x; rb < n_blocks; rb += kPm2Groups * gridDim.x, k += kPm2Groups) {
       const uint32_t use = k >> 1;
       const int grow = rb * kPmRows + row;        // global trajectory row
+      const long long tw0 = dbg ? clock64() : 0;
       umma::mbar_wait(bar_acc_full + grp, use & 1);
       __syncwarp();
       umma::tc_fence_after();
+      const long long t_start = dbg ? clock64() : 0;
+      if (dbg) w_full += t_start - tw0;
 
       if (a.mode != PM_BIAS) {
         // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26), two-pass
@@ -215,6 +247,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         }
       }
 
+      if (dbg) t_stats += clock64() - t_start;
       const int n_acc = a.n_groups + a.aux;
       const int rby_o = 2 * a.cout;               // output line bytes
       for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
@@ -316,7 +349,9 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       umma::tc_fence_before();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(bar_acc_empty + grp);
+      if (dbg) t_busy += clock64() - t_start;
     }
+    if (dbg && et == 0 && grp == 0) { dbg[6] = w_full; dbg[8] = t_busy; dbg[9] = t_stats; dbg[10] = 0; dbg[11] = t_busy - t_stats; dbg[12] = 0; }
     umma::tc_fence_before();
   }
   __syncthreads();
@@ -324,6 +359,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     umma::tc_fence_after();
     umma::tmem_dealloc<512>(tmem_base);
   }
+  if (dbg && threadIdx.x == 0) { dbg[1] = dbg[0]; dbg[7] = clock64(); }
 }
 
 }  // namespace edmp

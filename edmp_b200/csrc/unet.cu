@@ -327,6 +327,7 @@ struct Builder {
   std::vector<std::pair<std::string, int>> temb_blocks;  // (res-block prefix, offset)
   int temb_width = 0;
   bool ok = true;
+  std::string why;            // which plan check failed (for the error message)
 
   const float* P(const std::string& name) const { return params + pw->table.at(name).off; }
 
@@ -839,11 +840,12 @@ struct Builder {
     int cols = (t.n_groups + t.aux) * ntiles * pct, p2 = 32;
     while (p2 < cols) p2 *= 2;
     t.tmem_cols = p2;
-    ok = ok && p2 <= (u->pm2 ? 256 : 512);   // (persistent kernel: two accumulator buffers of 256 columns)
+    if (p2 > (u->pm2 ? 256 : 512)) { ok = false; why += " pm:tmem(" + ly.name + ")"; }   // (persistent kernel: two accumulator buffers of 256 columns)
+    if (u->pm2 && ntiles * t.n_terms * nkc * (C / 16) > kPm2MaxIssue) { ok = false; why += " pm:issue-table(" + ly.name + ")"; }
     ly.kind = LAYER_PM;
     ly.tc_smem = 1024 + std::max((((size_t)t.a_bytes_total + 1023) & ~(size_t)1023) + (size_t)nparts * t.w_bytes_part,
                                  tail_end) + 256;
-    ok = ok && ly.tc_smem <= 232448 - (u->pm2 ? 10240 : 6144) - 1024;
+    if (ly.tc_smem > (size_t)(232448 - (u->pm2 ? 13312 : 6144))) { ok = false; why += " pm:smem(" + ly.name + ")"; }
   }
 
   // Conv1dBlock (conv5 + GroupNorm + Mish [+ time embedding] [+ identity residual]) on the
@@ -1060,10 +1062,10 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -1197,7 +1199,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->temb = upload(u, table);
   b.ok = b.ok && u->temb;
   if (!b.ok) {
-    set_error("unet_create: allocation failed or an unsupported layer shape was requested");
+    set_error("unet_create: allocation failed or an unsupported layer shape was requested:" + b.why);
     unet_destroy(u);
     return 1;
   }
@@ -1345,7 +1347,7 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
                    (u->layers[op].kind == LAYER_TC || u->layers[op].kind == LAYER_PM || u->layers[op].kind == LAYER_TC2),
                "op is not a tensor-core layer");
   Layer& ly = u->layers[op];
-  const int ctas = ly.kind == LAYER_PM ? ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt)
+  const int ctas = ly.kind == LAYER_PM ? (u->pm2 ? std::min((rows + kPmRows - 1) / kPmRows, u->sm_count) : ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt))
                    : ly.kind == LAYER_TC2 ? (ly.cta_group == 2 ? 2 * std::min(((((rows + kTcRows - 1) / kTcRows) + 1) / 2) * ly.t2.n_col_tiles, u->sm_count / 2)
                                                                : std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count))
                                           : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
