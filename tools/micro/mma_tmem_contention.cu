@@ -1,0 +1,82 @@
+// Microbenchmark: does the epilogue's TMEM traffic (tcgen05.ld of another accumulator buffer) slow the MMAs down?
+// Warp 0 issues M=128 kind::f16 MMAs (hi/lo x3 pattern) into TMEM columns [0,256); `readers` other warps loop
+// tcgen05.ld.32x32b.x16 over columns [256,512) meanwhile.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../edmp_b200/csrc -o mma_tmem_contention mma_tmem_contention.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "umma.cuh"
+using namespace edmp::umma;
+
+__global__ void __launch_bounds__(576) k(int N, int iters, int readers, int sw64, long long* out, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&done, 1); fence_barrier_init(); stop = 0; }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const uint32_t a_base = smem_u32(smem), b_base = a_base + 65536;
+    uint64_t d0 = make_desc_sw128(0);
+    if (sw64) {   // 64-byte rows, SWIZZLE_64B, 8-row atoms of 512 B (the position-major kernels at C = 32)
+      d0 = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+    }
+    const uint32_t idesc = make_idesc(0, 128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint64_t da = d0 | (((a_base + (i & 15) * 2048) & 0x3FFFF) >> 4), db = d0 | ((b_base & 0x3FFFF) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          mma_bf16(tmem, da + 1024 + 2 * ks, db + 2 * ks, idesc, 1u);
+          mma_bf16(tmem, da + 2 * ks, db + 512 + 2 * ks, idesc, 1u);
+          mma_bf16(tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&done);
+    __syncwarp();
+    mbar_wait(&done, 0);
+    long long t2 = clock64();
+    if (lane == 0) { stop = 1; if (blockIdx.x == 0) out[0] = t2 - t0; }
+  } else if (warp >= 2 && warp < 2 + readers) {
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+    float acc = 0.f;
+    int u = warp >> 2;
+    while (!stop) {
+      float v[16];
+      tmem_ld16(t_lane + (uint32_t)((u & 15) * 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += v[j];
+      ++u;
+    }
+    if (acc == 123.456f) sink[0] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
+int main() {
+  long long* out; cudaMalloc(&out, 16);
+  float* sink; cudaMalloc(&sink, 16);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int sw64 : {0, 1})
+    for (int N : {32, 64, 128, 256})
+      for (int readers : {0, 4, 8, 16}) {
+        const int iters = 2048;
+        for (int rep = 0; rep < 2; ++rep) k<<<64, 576, 130 * 1024>>>(N, iters, readers, sw64, out, sink);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h = 0; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+        printf("%s N=%3d readers=%2d: %6.1f cyc/MMA (tensor floor %3d)  %s\n", sw64 ? "SW64 " : "SW128", N, readers, (double)h / (iters * 6), N / 2,
+               cudaGetErrorString(e));
+      }
+  return 0;
+}
