@@ -7,7 +7,7 @@
 #include "umma.cuh"
 using namespace edmp::umma;
 
-__global__ void __launch_bounds__(576) k(int N, int iters, int readers, int sw64, long long* out, float* sink) {
+__global__ void __launch_bounds__(576) k(int N, int iters, int readers, int sw64, int alu, long long* out, float* sink) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t done;
@@ -46,10 +46,34 @@ __global__ void __launch_bounds__(576) k(int N, int iters, int readers, int sw64
     mbar_wait(&done, 0);
     long long t2 = clock64();
     if (lane == 0) { stop = 1; if (blockIdx.x == 0) out[0] = t2 - t0; }
-  } else if (warp >= 2 && warp < 2 + readers) {
+  } else if (warp >= 2 && warp < 2 + readers && !(alu == 2 && (warp & 3) == 0)) {
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
     float acc = 0.f;
     int u = warp >> 2;
+    if (alu == 3) {
+      unsigned y0 = lane, y1 = lane + 1, y2 = lane + 2, y3 = lane + 3;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { y0 = y0 * 3u + 1u; y1 = (y1 ^ 0x5bd1e995u) + y0; y2 = y2 * 5u + 7u; y3 = (y3 ^ 0x9e3779b9u) + y2; }
+      }
+      acc = (float)(y0 + y1 + y2 + y3);
+    } else if (alu == 4) {
+      float x0 = (float)lane, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x0 = fmaf(x0, 1.0001f, 0.5f); x1 = fmaf(x1, 0.9999f, 0.25f); x2 = fmaf(x2, 1.0002f, 0.125f); x3 = fmaf(x3, 0.9998f, 0.0625f); }
+        __nanosleep(0);
+      }
+      acc = x0 + x1 + x2 + x3;
+    } else if (alu) {
+      // ALU-heavy neighbours (like epilogue warps in their Mish / split phase): dense dependent-free FMA streams
+      float x0 = (float)lane, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { x0 = fmaf(x0, 1.0001f, 0.5f); x1 = fmaf(x1, 0.9999f, 0.25f); x2 = fmaf(x2, 1.0002f, 0.125f); x3 = fmaf(x3, 0.9998f, 0.0625f); }
+      }
+      acc = x0 + x1 + x2 + x3;
+    } else
     while (!stop) {
       float v[16];
       tmem_ld16(t_lane + (uint32_t)((u & 15) * 16), v);
@@ -68,14 +92,15 @@ int main() {
   long long* out; cudaMalloc(&out, 16);
   float* sink; cudaMalloc(&sink, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int sw64 : {0, 1})
-    for (int N : {32, 64, 128, 256})
-      for (int readers : {0, 4, 8, 16}) {
+  for (int alu : {1, 2, 3, 4})
+  for (int sw64 : {0})
+    for (int N : {32, 128})
+      for (int readers : {0, 4, 16}) {
         const int iters = 2048;
-        for (int rep = 0; rep < 2; ++rep) k<<<64, 576, 130 * 1024>>>(N, iters, readers, sw64, out, sink);
+        for (int rep = 0; rep < 2; ++rep) k<<<64, 576, 130 * 1024>>>(N, iters, readers, sw64, alu, out, sink);
         cudaError_t e = cudaDeviceSynchronize();
         long long h = 0; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
-        printf("%s N=%3d readers=%2d: %6.1f cyc/MMA (tensor floor %3d)  %s\n", sw64 ? "SW64 " : "SW128", N, readers, (double)h / (iters * 6), N / 2,
+        printf("%s %s N=%3d neighbours=%2d: %6.1f cyc/MMA (tensor floor %3d)  %s\n", alu == 1 ? "FFMA all SMSPs   " : alu == 2 ? "FFMA other SMSPs " : alu == 3 ? "integer all SMSPs" : "FFMA + nanosleep ", sw64 ? "SW64 " : "SW128", N, readers, (double)h / (iters * 6), N / 2,
                cudaGetErrorString(e));
       }
   return 0;
