@@ -129,6 +129,25 @@ def test_unet_headline_batch_matches_small_batch(tmp_path_factory, sd):
             ref = unet_oracle.unet_forward(sd, x[idx], 200).numpy()
         assert np.abs(full[idx.to(DEV)].cpu().numpy() - ref).max() <= EPS_TOL[prec]
         assert torch.isfinite(full).all()
+        # the same (pair-layer) engine at a tiny batch: one row tile plus the pair's padding tile
+        few = big(x[:5].contiguous().to(DEV), 200)
+        assert (few - small(x[:5].contiguous().to(DEV), 200)).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 5e-5), ("f16", 3e-2), ("bf16", 2e-1)])
+def test_unet_other_16bit_modes_run_the_same_kernels(tmp_path_factory, sd, prec, tol, monkeypatch):
+    """The throughput-only arithmetic modes share the persistent kernels (BF16 elements, single-pass = no lo parts):
+    they must run (also on the CTA-pair path) and stay within their own, looser, distance of the oracle."""
+    x = torch.randn(300, 7, 50, generator=torch.Generator().manual_seed(8)) * 1.5
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, x, 77).numpy()
+    for pairs in ("0", "1"):
+        if pairs == "1":
+            monkeypatch.setenv("EDMP_CG2", "1")
+        m = _model(tmp_path_factory, sd, prec)
+        eps = m(x.to(DEV), 77).cpu().numpy()
+        assert np.isfinite(eps).all()
+        assert np.abs(eps - ref).max() <= tol, (prec, pairs, np.abs(eps - ref).max())
 
 
 def test_unet_headline_batch_is_deterministic(tmp_path_factory, sd):
