@@ -45,6 +45,12 @@ SIGNATURES = {
     "edmp_sdf_scene_destroy": (None, [c_void_p]),
     "edmp_sdf_guide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "edmp_sdf_cloud_clearance": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "edmp_metrics_nfft": (c_int, [c_int, c_int]),
+    "edmp_ee_transform": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "edmp_trajectory_metrics": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double, c_double, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "edmp_sparc": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                           c_void_p]),
 }
 
 _lib = None

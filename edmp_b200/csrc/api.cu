@@ -8,6 +8,7 @@
 #include "guide.h"
 #include "sampler.h"
 #include "sdf_guide.h"
+#include "metrics.h"
 #include "unet.h"
 
 namespace edmp {
@@ -178,5 +179,24 @@ int edmp_sdf_cloud_clearance(const float* q_d, int n, int rows, const float* poi
                              float* clearance_d, void* stream) {
   if (!q_d || !points_d || !clearance_d) { set_error("edmp_sdf_cloud_clearance: null argument"); return 2; }
   EDMP_TRY(sdf_cloud_launch(q_d, n, rows, points_d, n_points, clearance_d, (cudaStream_t)stream));
+}
+
+/* ---- trajectory metrics ----------------------------------------------------- */
+int edmp_metrics_nfft(int m, int padlevel) { return metrics_nfft(m, padlevel); }
+int edmp_ee_transform(const float* q_d, int rows, int n, float* T_d, void* stream) {
+  if (!q_d || !T_d) { set_error("edmp_ee_transform: null argument"); return 2; }
+  EDMP_TRY(ee_transform_launch(q_d, rows, n, T_d, (cudaStream_t)stream));
+}
+int edmp_trajectory_metrics(const double* traj_d, int rows, int n, double dt, int padlevel, double fc, double amp_th,
+                            double* out_d, double* spectrum_d, int* selected_d, void* stream) {
+  if (!traj_d || !out_d) { set_error("edmp_trajectory_metrics: null argument"); return 2; }
+  EDMP_TRY(trajectory_metrics_launch(traj_d, rows, n, dt, padlevel, fc, amp_th, out_d, spectrum_d, selected_d,
+                                     (cudaStream_t)stream));
+}
+int edmp_sparc(const double* movement_d, int rows, int m, double fs, int padlevel, double fc, double amp_th,
+               double* sal_d, double* spectrum_d, int* selected_d, void* stream) {
+  if (!movement_d || !sal_d) { set_error("edmp_sparc: null argument"); return 2; }
+  EDMP_TRY(sparc_launch(movement_d, rows, m, fs, padlevel, fc, amp_th, sal_d, spectrum_d, selected_d,
+                        (cudaStream_t)stream));
 }
 }  // extern "C"

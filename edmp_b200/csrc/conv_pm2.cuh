@@ -205,9 +205,11 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         const float inv_n = 1.0f / (float)(CG * a.n_m);
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-          float s[NG];
+          // (dense fp32 math in packed f32x2 form, see umma.cuh f2::; a pair of neighbouring channels shares its group)
+          f2::f32x2 s2[NG];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) s[g] = 0.0f;
+          for (int g = 0; g < NG; ++g) s2[g] = f2::dup(0.0f);
+          const f2::f32x2 sc2 = f2::dup(a.acc_scale);
           for (int mt = half; mt < ntiles; mt += 2) {
             const bool valid = (16 * mt + pos_in_tile) < a.n_m;
 #pragma unroll
@@ -217,15 +219,18 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
               pm_ld_par16(s_par + u * 16, b);
               if (valid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int g = u * GPU_ + i / CG;
-                  const float y = fmaf(v[i], a.acc_scale, b[i]);
-                  if (pass == 0) s[g] += y;
-                  else { const float d = y - mr[0][row][g]; s[g] = fmaf(d, d, s[g]); }
+                for (int i = 0; i < 8; ++i) {
+                  const int g = u * GPU_ + (2 * i) / CG;
+                  const f2::f32x2 y = f2::fma(f2::pk(v[2 * i], v[2 * i + 1]), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
+                  if (pass == 0) s2[g] = f2::add(s2[g], y);
+                  else { const f2::f32x2 d = f2::sub(y, f2::dup(mr[0][row][g])); s2[g] = f2::fma(d, d, s2[g]); }
                 }
               }
             }
           }
+          float s[NG];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) s[g] = f2::hsum(s2[g]);
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             s[g] += __shfl_xor_sync(0xffffffffu, s[g], 8);
@@ -262,9 +267,9 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
           const bool valid = idx < a.n_m && grow < a.rows;
           const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
           const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
-          float fin[7];
+          f2::f32x2 fin2[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) fin[j] = 0.0f;
+          for (int j = 0; j < 7; ++j) fin2[j] = f2::dup(0.0f);
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
             float v[16];
@@ -280,11 +285,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
                 rl[m] = a.res.lo ? *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off) : make_uint4(0, 0, 0, 0);
               }
             }
+            f2::f32x2 v2[8];
             {
               float b[16];
               pm_ld_par16(pb + u * 16, b);
+              const f2::f32x2 sc2 = f2::dup(sc);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sc, b[i]);
+              for (int i = 0; i < 8; ++i) v2[i] = f2::fma(f2::pk(v[2 * i], v[2 * i + 1]), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
             }
             if (gn) {
               float ga[16], be[16], te[16];
@@ -292,10 +299,11 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
               pm_ld_par16(s_par + 128 + u * 16, be);
               pm_ld_par16(s_par + 192 + u * 16, te);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int g = u * GPU_ + i / CG;
-                const float t = (v[i] - mr[0][row][g]) * mr[1][row][g] * ga[i] + be[i];
-                v[i] = pm_mish(t) + te[i];
+              for (int i = 0; i < 8; ++i) {
+                const int g = u * GPU_ + (2 * i) / CG;
+                const f2::f32x2 A = f2::mul(f2::dup(mr[1][row][g]), f2::pk(ga[2 * i], ga[2 * i + 1]));
+                const f2::f32x2 t = f2::fma(f2::sub(v2[i], f2::dup(mr[0][row][g])), A, f2::pk(be[2 * i], be[2 * i + 1]));
+                v2[i] = f2::mish_add(t, f2::pk(te[2 * i], te[2 * i + 1]));
               }
             }
             if (!valid) continue;
@@ -305,12 +313,12 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
                 float x[8];
                 tc_chunk_sum<EL>(rh[m], rl[m], a.res.lo != nullptr, x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[m * 8 + e] += x[e];
+                for (int e = 0; e < 4; ++e) v2[m * 4 + e] = f2::add(v2[m * 4 + e], f2::pk(x[2 * e], x[2 * e + 1]));
               }
             }
             if (o_hi || (!is_aux && a.tc_hi)) {
               uint4 h[4], l[4];
-              tc_split_store<EL>(v, (is_aux ? a.aux_lo : (a.tc_hi ? a.tc_lo : a.out_lo)) != nullptr, h, l);
+              tc_split_store2<EL>(v2, (is_aux ? a.aux_lo : (a.tc_hi ? a.tc_lo : a.out_lo)) != nullptr, h, l);
               if (o_hi) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
@@ -336,12 +344,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 7; ++j)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) fin[j] = fmaf(s_fw[j * COUT + u * 16 + i], v[i], fin[j]);
+                for (int i = 0; i < 8; ++i)
+                  fin2[j] = f2::fma(f2::pk(s_fw[j * COUT + u * 16 + 2 * i], s_fw[j * COUT + u * 16 + 2 * i + 1]), v2[i], fin2[j]);
             }
           }
           if (valid && !is_aux && a.eps) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) a.eps[((size_t)grow * 7 + j) * a.lout + lo] = fin[j] + s_fw[7 * COUT + j];
+            for (int j = 0; j < 7; ++j) a.eps[((size_t)grow * 7 + j) * a.lout + lo] = f2::hsum(fin2[j]) + s_fw[7 * COUT + j];
           }
         }
       }

@@ -173,6 +173,26 @@ __device__ __forceinline__ void tc_split_store(const float (&v)[16], bool want_l
   }
 }
 
+// 16-bit element types: split 16 fp32 values held as 8 packed pairs into hi/lo parts; writes two 16-byte chunks each
+template <int EL>
+__device__ __forceinline__ void tc_split_store2(const f2::f32x2 (&v2)[8], bool want_lo, uint4* hi, uint4* lo) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x0, x1, d0, d1;
+      f2::upk(v2[m * 4 + e], x0, x1);
+      h[e] = pack16x2<EL>(x0, x1);
+      const float2 hf = unpack16x2<EL>(h[e]);
+      f2::upk(f2::sub(v2[m * 4 + e], f2::pk(hf.x, hf.y)), d0, d1);
+      l[e] = want_lo ? pack16x2<EL>(d0, d1) : 0u;
+    }
+    hi[m] = make_uint4(h[0], h[1], h[2], h[3]);
+    lo[m] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // sum of the hi and lo 16-byte chunks as fp32 values (4 for TF32, 8 for BF16)
 template <int EL>
 __device__ __forceinline__ void tc_chunk_sum(const uint4& h, const uint4& l, bool has_lo, float* out) {

@@ -515,7 +515,6 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       };
       if (a.mode != TC_BIAS) {
         // GroupNorm(8) over (cg channels x L positions) of this row (blocks.py:24-26).  Every 16-column unit (8-column
-        // half when groups have 8 channels) yields an exact two-pass (mean, M2) on registers; the pieces of a group
         // meet in shared memory among the four warps of this lane quarter and are combined with
         // M2 = sum M2_i + n_i * sum (mean_i - mean)^2 -- no E[x^2] - mean^2 cancellation anywhere.
 #pragma unroll 1
@@ -533,21 +532,25 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             if (u < n_units) {
               int lo, c0;
               unit_pos(u << 4, lo, c0);
-              float v[16], b[16];
+              float b[16];
               pm_ld_par16(s_par + c0, b);
-              float s0 = 0.0f, s1 = 0.0f;
+              const f2::f32x2 sc2 = f2::dup(sc0);
+              f2::f32x2 v2[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                v[i] = fmaf(__uint_as_float(raw[j][i]), sc0, b[i]);
-                if (i < 8) s0 += v[i]; else s1 += v[i];
-              }
+              for (int i = 0; i < 8; ++i)
+                v2[i] = f2::fma(f2::pku(raw[j][2 * i], raw[j][2 * i + 1]), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
+              const float s0 = f2::hsum(f2::add(f2::add(v2[0], v2[1]), f2::add(v2[2], v2[3])));
+              const float s1 = f2::hsum(f2::add(f2::add(v2[4], v2[5]), f2::add(v2[6], v2[7])));
               const float m0 = two ? s0 * 0.125f : (s0 + s1) * 0.0625f, m1 = two ? s1 * 0.125f : m0;
-              float q0 = 0.0f, q1 = 0.0f;
+              const f2::f32x2 mm0 = f2::dup(m0), mm1 = f2::dup(m1);
+              f2::f32x2 qa = f2::dup(0.0f), qb = f2::dup(0.0f);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float d = v[i] - (i < 8 ? m0 : m1);
-                if (i < 8) q0 = fmaf(d, d, q0); else q1 = fmaf(d, d, q1);
+              for (int i = 0; i < 4; ++i) {
+                const f2::f32x2 da = f2::sub(v2[i], mm0), db = f2::sub(v2[4 + i], mm1);
+                qa = f2::fma(da, da, qa);
+                qb = f2::fma(db, db, qb);
               }
+              const float q0 = f2::hsum(qa), q1 = f2::hsum(qb);
               if (two) {
                 my_part[(2 * u) * 256] = m0; my_part[(2 * u) * 256 + 128] = q0;
                 my_part[(2 * u + 1) * 256] = m1; my_part[(2 * u + 1) * 256 + 128] = q1;
@@ -657,13 +660,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             const int chunk = (kk & (E::kCpc - 1)) >> 3;          // 16-byte chunk inside the 128-byte row
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-              float v[8];
+              // (all dense fp32 math in packed f32x2 form, see umma.cuh f2::)
+              f2::f32x2 v2[4];
               {
                 const float* pb0 = s_par + c0 + m * 8;
                 const float4 z0 = *reinterpret_cast<const float4*>(pb0), z1 = *reinterpret_cast<const float4*>(pb0 + 4);
-                const float bi[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                const f2::f32x2 sc2 = f2::dup(sc0);
+                const f2::f32x2 bi[4] = {f2::pk(z0.x, z0.y), f2::pk(z0.z, z0.w), f2::pk(z1.x, z1.y), f2::pk(z1.z, z1.w)};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(yr[j][m * 8 + e]), sc0, bi[e]);
+                for (int e = 0; e < 4; ++e) v2[e] = f2::fma(f2::pku(yr[j][m * 8 + 2 * e], yr[j][m * 8 + 2 * e + 1]), sc2, bi[e]);
               }
               if (a.mode != TC_BIAS) {
                 const float m_ = (two && m) ? mean[j][1] : mean[j][0], r_ = (two && m) ? rstd[j][1] : rstd[j][0];
@@ -671,33 +676,40 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 const float4 g0 = *reinterpret_cast<const float4*>(pg), g1 = *reinterpret_cast<const float4*>(pg + 4);
                 const float4 b0 = *reinterpret_cast<const float4*>(pg + 128), b1 = *reinterpret_cast<const float4*>(pg + 132);
                 const float4 e0 = *reinterpret_cast<const float4*>(pg + 256), e1 = *reinterpret_cast<const float4*>(pg + 260);
-                const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float te[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                const f2::f32x2 ga[4] = {f2::pk(g0.x, g0.y), f2::pk(g0.z, g0.w), f2::pk(g1.x, g1.y), f2::pk(g1.z, g1.w)};
+                const f2::f32x2 be[4] = {f2::pk(b0.x, b0.y), f2::pk(b0.z, b0.w), f2::pk(b1.x, b1.y), f2::pk(b1.z, b1.w)};
+                const f2::f32x2 te[4] = {f2::pk(e0.x, e0.y), f2::pk(e0.z, e0.w), f2::pk(e1.x, e1.y), f2::pk(e1.z, e1.w)};
+                const f2::f32x2 mm = f2::dup(m_), rr2 = f2::dup(r_);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = t2::mish((v[e] - m_) * (r_ * ga[e]) + be[e]) + te[e];
+                for (int e = 0; e < 4; ++e)
+                  v2[e] = f2::mish_add(f2::fma(f2::sub(v2[e], mm), f2::mul(rr2, ga[e]), be[e]), te[e]);
               }
               if (a.mode == TC_GN_RES_PW) {
                 const float* pb = s_par + 512 + c0 + m * 8;
                 const float4 q0 = *reinterpret_cast<const float4*>(pb), q1 = *reinterpret_cast<const float4*>(pb + 4);
-                const float br[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                const f2::f32x2 br[4] = {f2::pk(q0.x, q0.y), f2::pk(q0.z, q0.w), f2::pk(q1.x, q1.y), f2::pk(q1.z, q1.w)};
+                const f2::f32x2 sc12 = f2::dup(sc1);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += fmaf(__uint_as_float(rr[j][m * 8 + e]), sc1, br[e]);
+                for (int e = 0; e < 4; ++e)
+                  v2[e] = f2::add(v2[e], f2::fma(f2::pku(rr[j][m * 8 + 2 * e], rr[j][m * 8 + 2 * e + 1]), sc12, br[e]));
               } else if (a.mode == TC_GN_RES_ID) {
                 float x[8];
                 tc_chunk_sum<EL>(make_uint4(rr[j][4 * m], rr[j][4 * m + 1], rr[j][4 * m + 2], rr[j][4 * m + 3]),
                                  make_uint4(rr[j][8 + 4 * m], rr[j][8 + 4 * m + 1], rr[j][8 + 4 * m + 2], rr[j][8 + 4 * m + 3]),
                                  a.res.lo != nullptr, x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += x[e];
+                for (int e = 0; e < 4; ++e) v2[e] = f2::add(v2[e], f2::pk(x[2 * e], x[2 * e + 1]));
               }
               // hi/lo split of 8 values -> one 16-byte chunk each
               uint32_t hh[4], ll[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                hh[e] = pack16x2<EL>(v[2 * e], v[2 * e + 1]);
+                float x0, x1, d0, d1;
+                f2::upk(v2[e], x0, x1);
+                hh[e] = pack16x2<EL>(x0, x1);
                 const float2 hf = unpack16x2<EL>(hh[e]);
-                ll[e] = pack16x2<EL>(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                f2::upk(f2::sub(v2[e], f2::pk(hf.x, hf.y)), d0, d1);
+                ll[e] = pack16x2<EL>(d0, d1);
               }
               if (grow < a.rows) {
                 size_t dst;

@@ -151,4 +151,38 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 }  // namespace umma
+
+// Packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per lane and instruction; the
+// per-lane results are those of the scalar instructions).  The epilogues use it for all their dense fp32 math: an
+// epilogue warp that can issue an fma-pipe instruction EVERY cycle starves an MMA-issuing warp on the same SM
+// sub-partition (tools/micro/mma_tmem_contention.cu, profiles/micro/r1_mma_issue_vs_neighbour_instruction_mix.txt:
+// 41 -> 110 / 270 / 1100 cycles per tcgen05.mma next to 1 / 2 / 4 FFMA-dense warps, 41 -> 43 next to FFMA2-dense
+// warps doing the same flops), and it halves the epilogue's own instruction count.
+namespace f2 {
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pku(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ f32x2 dup(float x) { return pk(x, x); }
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float hsum(f32x2 v) { float a, b; upk(v, a, b); return a + b; }
+// Mish(x) + addend for two values: x * n / (n + 2) with n = e^x (e^x + 2) (single-instruction ex2 / rcp approximations,
+// relative error ~1e-7 each; clamping x at 20 makes n / (n + 2) round to exactly 1)
+__device__ __forceinline__ f32x2 mish_add(f32x2 x, f32x2 addend) {
+  float x0, x1, t0, t1, e0, e1, d0, d1, r0, r1;
+  upk(x, x0, x1);
+  upk(mul(pk(fminf(x0, 20.0f), fminf(x1, 20.0f)), dup(1.4426950408889634f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  const f32x2 e = pk(e0, e1), two = dup(2.0f);
+  const f32x2 n = mul(e, add(e, two));
+  upk(add(n, two), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return fma(x, mul(n, pk(r0, r1)), addend);
+}
+}  // namespace f2
 }  // namespace edmp

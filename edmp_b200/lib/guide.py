@@ -66,6 +66,21 @@ class IntersectionVolumeGuide:
         # 'batch channels traj_len -> batch traj_len channels' (lib/guide.py:43)
         return x.permute(0, 2, 1)
 
+    def get_end_effector_transform(self, joints):
+        """[b, n, 7] joint tensor -> float32 [b, n, 4, 4] end-effector transforms on the guide's device: the product
+        of the 10 DH matrices (reference lib/guide.py:100-116)."""
+        dev = _lib.require_cuda(self.device)
+        q = torch.as_tensor(joints).to(dev, torch.float32).contiguous()
+        if q.dim() != 3 or q.shape[2] != 7:
+            raise ValueError("joints must be [batch, traj_len, 7]")
+        b, n = int(q.shape[0]), int(q.shape[1])
+        with torch.cuda.device(dev):
+            T = torch.empty(b, n, 4, 4, device=dev, dtype=torch.float32)
+            _lib.check(_lib.load().edmp_ee_transform(ctypes.c_void_p(q.data_ptr()), b, n,
+                                                     ctypes.c_void_p(T.data_ptr()), _lib.stream_ptr()),
+                       "edmp_ee_transform")
+        return T
+
     # ---- engine --------------------------------------------------------------------------------------
     def _scene_handle(self):
         if self._scene is None:

@@ -168,6 +168,25 @@ int edmp_sdf_guide(edmp_sdf_scene* s, const float* q_d, int n, int rows, float m
 int edmp_sdf_cloud_clearance(const float* q_d, int n, int rows, const float* points_d, int n_points,
                              float* clearance_d, void* stream);
 
+/* ---- trajectory metrics for whole ensembles ----------------------------------------
+ * Replaces the per-trajectory host code of the reference's lib/metrics.py (MetricsCalculator).  All pointers are
+ * device pointers. */
+/* nfft = 2^(ceil(log2 m) + padlevel) of an m-sample profile (lib/metrics.py:90); 0 if out of range */
+int edmp_metrics_nfft(int m, int padlevel);
+/* lib/guide.py:100-116 get_end_effector_transform: q_d float32 [rows,n,7] -> T_d float32 [rows,n,4,4] = product of
+ * the 10 DH matrices (get_tf_mat :45-72, static table :29-38) */
+int edmp_ee_transform(const float* q_d, int rows, int n, float* T_d, void* stream);
+/* lib/metrics.py:11-45: traj_d float64 [rows,7,n] (n <= 64) -> out_d float64 [rows,4] = joint path length,
+ * end-effector path length, joint SPARC, end-effector SPARC (speed profiles norm(diff / dt), fs = 1 / dt).
+ * spectrum_d (may be null) float64 [rows,2,nfft]: normalised magnitude spectra Mf of the two profiles;
+ * selected_d (may be null) int [rows,2,2]: first / last bin of the arc (-1, -1: empty selection). */
+int edmp_trajectory_metrics(const double* traj_d, int rows, int n, double dt, int padlevel, double fc, double amp_th,
+                            double* out_d, double* spectrum_d, int* selected_d, void* stream);
+/* lib/metrics.py:47-130 sparc(movement, fs, padlevel, fc, amp_th) for a batch of raw profiles: movement_d float64
+ * [rows,m] -> sal_d [rows]; spectrum_d [rows,nfft] and selected_d [rows,2] may be null. */
+int edmp_sparc(const double* movement_d, int rows, int m, double fs, int padlevel, double fc, double amp_th,
+               double* sal_d, double* spectrum_d, int* selected_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

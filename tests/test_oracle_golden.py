@@ -176,3 +176,28 @@ def test_sdf_oracle_gradient_is_consistent():
         qm[b, j, w] -= h
         fd = (sdfo.evaluate(qp, boxes, cyls, 0.05, False)[0][b] - sdfo.evaluate(qm, boxes, cyls, 0.05, False)[0][b]) / (2 * h)
         assert abs(fd - grad[b, j, w]) <= 1e-5 * max(1.0, abs(fd))
+
+
+# ---- trajectory metrics: oracle/metrics_oracle.py against the reference's MetricsCalculator ----
+def test_metrics_oracle_matches_reference(golden):
+    from oracle import metrics_oracle as mo
+    g = golden("metrics.npz")
+    traj, dts = g["traj"], g["dts"]
+    T = mo.ee_transforms(np.transpose(traj, (0, 2, 1)))
+    np.testing.assert_allclose(T, g["ee_transforms"], rtol=0, atol=1e-6)
+    for r in range(traj.shape[0]):
+        np.testing.assert_allclose(mo.path_lengths(traj[r]), g["path_lengths"][r], rtol=1e-6, atol=1e-7)
+        for i, dt in enumerate(dts):
+            m = mo.trajectory_metrics(traj[r], float(dt))
+            # SPARC is a float32 FFT inside the reference for the end-effector profile: 1e-5 relative
+            np.testing.assert_allclose(m[2:], g["sparc"][i, r], rtol=1e-5, atol=1e-7)
+    sal, f, Mf, first, last = mo.sparc(mo.speed_profiles(traj[0], float(dts[0]))[0], 1. / float(dts[0]))
+    np.testing.assert_allclose(f, g["f"], rtol=0, atol=0)
+    np.testing.assert_allclose(Mf, g["Mf_joint"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(f[first:last + 1], g["fsel_joint"])
+    # the known-answer example in the reference's docstring (lib/metrics.py:79-84): '%.5f' % sal == '-1.41403'
+    ex = mo.sparc(g["example_move"], 100.)[0]
+    assert "%.5f" % ex == "-1.41403"
+    np.testing.assert_allclose(ex, float(g["example_sal"]), rtol=1e-12)
+    # all-zero movement -> 0 (lib/metrics.py:86-88)
+    assert mo.sparc(np.zeros(49), 50.)[0] == 0.0

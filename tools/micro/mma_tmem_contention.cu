@@ -69,6 +69,51 @@ __global__ void __launch_bounds__(576) k(int N, int iters, int readers, int sw64
         __nanosleep(0);
       }
       acc = x0 + x1 + x2 + x3;
+    } else if (alu == 5) {   // MUFU-dense (ex2.approx): 4 independent chains
+      float x0 = (float)lane * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x2)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x3));
+        }
+      }
+      acc = x0 + x1 + x2 + x3;
+    } else if (alu == 6) {   // packed FP32x2 FMA (fma.rn.f32x2): same flops as mode 1 in half the instructions
+      unsigned long long p0 = 0x3f8000003f800000ull + lane, p1 = p0 + 1, p2 = p0 + 2, p3 = p0 + 3;
+      const unsigned long long m = 0x3f8003473f800347ull, c = 0x3f0000003f000000ull;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(m), "l"(c));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(m), "l"(c));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p2) : "l"(m), "l"(c));
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p3) : "l"(m), "l"(c));
+        }
+      }
+      acc = (float)(p0 + p1 + p2 + p3);
+    } else if (alu == 7) {   // one dependent FFMA chain (issues every ~4 cycles)
+      float x0 = (float)lane;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) x0 = fmaf(x0, 1.0001f, 0.5f);
+      }
+      acc = x0;
+    } else if (alu == 8) {   // FADD / FMUL mix without FFMA
+      float x0 = (float)lane, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { x0 = x0 + 0.5f; x1 = x1 * 0.9999f; x2 = x2 + 0.125f; x3 = x3 * 0.9998f; }
+      }
+      acc = x0 + x1 + x2 + x3;
+    } else if (alu == 9) {   // shared-memory loads (LDS.128) + a little math, like the parameter fetches of the epilogue
+      float x0 = 0.f;
+      const float4* sp = reinterpret_cast<const float4*>(smem + 100 * 1024) + lane;
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float4 v = sp[(j & 7) * 32]; x0 += v.x + v.y + v.z + v.w; }
+      }
+      acc = x0;
     } else if (alu) {
       // ALU-heavy neighbours (like epilogue warps in their Mish / split phase): dense dependent-free FMA streams
       float x0 = (float)lane, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
@@ -96,16 +141,16 @@ int main() {
   long long* out; cudaMalloc(&out, 16);
   float* sink; cudaMalloc(&sink, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int mma_w : {0, 17})
-  for (int alu : {1, 2, 3, 4})
+  for (int mma_w : {0})
+  for (int alu : {1, 5, 6, 7, 8, 9})
   for (int sw64 : {0})
     for (int N : {32, 128})
-      for (int readers : {0, 4, 16}) {
+      for (int readers : {0, 4, 8, 16}) {
         const int iters = 2048;
         for (int rep = 0; rep < 2; ++rep) k<<<64, 576, 130 * 1024>>>(N, iters, readers, sw64, alu, mma_w, out, sink);
         cudaError_t e = cudaDeviceSynchronize();
         long long h = 0; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
-        printf("issuer warp %2d  %s %s N=%3d neighbours=%2d: %6.1f cyc/MMA (tensor floor %3d)  %s\n", mma_w, alu == 1 ? "FFMA all SMSPs   " : alu == 2 ? "FFMA other SMSPs " : alu == 3 ? "integer all SMSPs" : "FFMA + nanosleep ", sw64 ? "SW64 " : "SW128", N, readers, (double)h / (iters * 6), N / 2,
+        printf("issuer warp %2d  %s %s N=%3d neighbours=%2d: %6.1f cyc/MMA (tensor floor %3d)  %s\n", mma_w, alu == 1 ? "FFMA all SMSPs   " : alu == 2 ? "FFMA other SMSPs " : alu == 3 ? "integer all SMSPs" : alu == 4 ? "FFMA + nanosleep " : alu == 5 ? "MUFU ex2         " : alu == 6 ? "FFMA2 (f32x2)    " : alu == 7 ? "FFMA one chain   " : alu == 8 ? "FADD/FMUL        " : "LDS.128 + FADD   ", sw64 ? "SW64 " : "SW128", N, readers, (double)h / (iters * 6), N / 2,
                cudaGetErrorString(e));
       }
   return 0;
