@@ -28,6 +28,16 @@ class RobotEnvironment:
     def spawn_collision_cylinders(self, cylinder_config):
         pass
 
+    def validate_ensemble(self, obstacle_config, trajectories, cylinders=None):
+        """Batched collision validation of sampled trajectories: [B,7,n] -> bool [B], True =
+        collision free.  GPU sphere / signed-distance check with the semantics of the reference's validation step
+        (mpinets/model.py:281-312) -- a fast stand-in for the sleep-bound PyBullet rollout of
+        lib/environment.py:632-680, not a physics replay.  obstacle_config rows are (xyz, quaternion xyzw, dims)."""
+        from .sdf_guide import SphereSDFGuide
+        device = self._guide.device if self._guide is not None else "cuda:0"
+        checker = SphereSDFGuide(obstacle_config, cylinders, device)
+        return ~checker.has_collision(trajectories).cpu().numpy()
+
     def benchmark_trajectory(self, trajectory):
         """1 if the trajectory's swept link boxes miss every obstacle box, else 0."""
         if self._guide is None:

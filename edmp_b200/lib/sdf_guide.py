@@ -66,6 +66,12 @@ class SphereSDFGuide:
     def clearance(self, q):
         return self.evaluate(q, False, True)[2]
 
+    def has_collision(self, q):
+        """[B,7,n] -> bool [B] (CUDA): the rollout collision predicate of the reference's validation step
+        (mpinets/model.py:296-312): some collision sphere at some waypoint has scene sdf <= its radius, i.e. the
+        trajectory's minimum clearance is <= 0.  One launch for the whole ensemble."""
+        return (self.clearance(q) <= 0.0).any(dim=1)
+
     def cloud_clearance(self, points, q):
         """points: [P,3] scene point cloud -> [B,n] nearest (sphere surface, point) distance per waypoint."""
         dev = _lib.require_cuda(self.device)

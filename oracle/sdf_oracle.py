@@ -168,6 +168,19 @@ def evaluate(q, boxes, cyls, margin=0.03, want_grad=True):
     return cost.detach().numpy(), grad, (sdf - r).min(dim=-1).values.detach().numpy()
 
 
+def has_collision(q, boxes, cyls):
+    """q [B,7,n] -> bool [B]: the rollout collision predicate of the reference's validation step
+    (mpinets/model.py:296-312): per sphere radius, some sphere centre at some waypoint has scene sdf <= radius."""
+    q = torch.tensor(np.asarray(q, dtype=np.float64))
+    c, r = sphere_centres(q.permute(0, 2, 1))                  # [B,n,59,3], [59]
+    sdf = scene_sdf(c, boxes, cyls)                            # [B,n,59]
+    hit = torch.zeros(q.shape[0], dtype=torch.bool)
+    for radius in sorted(set(r.tolist())):
+        sel = r == radius
+        hit = torch.logical_or(hit, torch.any(sdf[:, :, sel].reshape(q.shape[0], -1) <= radius, dim=-1))
+    return hit.numpy()
+
+
 def cloud_clearance(q, points):
     """q [B,7,n], points [P,3] -> [B,n] = min over (sphere, point) of |centre - p| - radius"""
     q = torch.tensor(np.asarray(q, dtype=np.float64))

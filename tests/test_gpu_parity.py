@@ -497,3 +497,24 @@ def test_sdf_cloud_clearance_matches_oracle():
         q = _sdf_trajs(rows, n, seed=10 + rows)
         got = guide.cloud_clearance(pts, q).cpu().numpy()
         np.testing.assert_allclose(got, sdfo.cloud_clearance(q, pts), rtol=0, atol=3e-6)
+
+
+def test_sdf_collision_predicate_matches_oracle():
+    """batched collision validation (mpinets/model.py:296-312 predicate) of an ensemble."""
+    from edmp_b200.lib import RobotEnvironment, SphereSDFGuide
+    from oracle import sdf_oracle as sdfo
+    boxes = np.array([[0.55, 0.0, 0.25, 0, 0, 0, 1, 0.25, 0.7, 0.5], [0.0, 0.55, 0.4, 0, 0, 0.3826834, 0.9238795, 0.3, 0.2, 0.8],
+                      [-0.4, -0.3, 0.6, 0, 0, 0, 1, 0.2, 0.2, 0.2]])
+    cyls = np.array([[0.3, -0.5, 0.3, 0, 0, 0, 1, 0.08, 0.6]])
+    q = _sdf_trajs(256, 50, seed=21)
+    q[:96] = scenes.START[None, :, None] + 0.05 * np.random.default_rng(1).normal(size=(96, 7, 50))   # partly free rows
+    want = sdfo.has_collision(q, boxes, cyls)
+    assert 20 < want.sum() < len(want) - 20               # both outcomes occur
+    got = SphereSDFGuide(boxes, cyls, DEV).has_collision(q).cpu().numpy()
+    # float32 kernel vs float64 oracle: rows whose minimum clearance is within 1e-5 m of zero could flip
+    _, _, clr = sdfo.evaluate(q, boxes, cyls, want_grad=False)
+    decided = np.abs(clr.min(axis=1)) > 1e-5
+    assert decided.sum() >= len(want) - 2
+    np.testing.assert_array_equal(got[decided], want[decided])
+    free = RobotEnvironment(gui=False).validate_ensemble(boxes, q, cylinders=cyls)
+    np.testing.assert_array_equal(free, ~got)
