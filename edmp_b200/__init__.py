@@ -6,6 +6,6 @@ the reference-shaped classes; all arithmetic of the hot path runs in libedmp_b20
 from .diffusion import Diffusion, TemporalUNet          # noqa: F401
 from .lib import IntersectionVolumeGuide                 # noqa: F401
 from .guide_cfg import Guide, YamlConfig, build_guide_cfgs, load_guide_hparams  # noqa: F401
-from . import synthetic                                  # noqa: F401
+from . import scene, synthetic                           # noqa: F401
 
 __version__ = "0.1.0"

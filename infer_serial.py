@@ -29,10 +29,11 @@ if ROOT not in sys.path:
 
 from edmp_b200 import (Diffusion, IntersectionVolumeGuide, TemporalUNet, YamlConfig, build_guide_cfgs,  # noqa: E402
                        load_guide_hparams, synthetic)
+from edmp_b200 import scene as front_end  # noqa: E402
 from edmp_b200.lib import MetricsCalculator, RobotEnvironment  # noqa: E402
 
 DIMS = (32, 64, 128, 256, 512, 512)        # reference infer_serial.py:50
-GOAL_TRUST_REGION = 0.0008                 # reference infer_serial.py:125 (hard-coded there too)
+GOAL_TRUST_REGION = front_end.GOAL_TRUST_REGION   # reference infer_serial.py:125 (hard-coded there too)
 
 
 class SyntheticProblems:
@@ -91,14 +92,10 @@ def load_model(cfg, device, precision):
 
 
 def pick_goal(guide, start, ik_goals):
-    """Goal filter of the reference (infer_serial.py:119-129): keep the candidates whose t=0 intersection volume is
-    within the trust region of the best one, then take the one nearest to the start in joint space."""
-    k = ik_goals.shape[0]
-    vol = guide.cost(torch.tensor(ik_goals[:, :, None], dtype=torch.float32), 0, batch_size=k)
-    vol = vol.sum(dim=(1, 2)).cpu().numpy()
-    keep = np.flatnonzero(vol < vol.min() + GOAL_TRUST_REGION)
-    dist = np.linalg.norm(ik_goals[keep] - start[None, :], axis=1)
-    return ik_goals[keep[int(np.argmin(dist))]], vol
+    """Goal filter of the reference (infer_serial.py:119-129), see edmp_b200.scene."""
+    vol = front_end.goal_volumes(guide, ik_goals)
+    goal, _ = front_end.select_goal(vol, start, ik_goals, GOAL_TRUST_REGION)
+    return goal, vol
 
 
 def main(argv=None):

@@ -129,3 +129,49 @@ def test_infer_serial_cfg_surface():
     assert shipped["guide"]["guides"] == [1, 2, 3, 4, 5, 10, 11, 13, 14, 16, 18, 21]
     with pytest.raises(SystemExit):
         infer_serial.load_problems(shipped)   # 'hybrid' needs the reference's loader + downloads
+
+
+def test_obstacle_flattening_like_the_reference_loader():
+    """edmp_b200.scene.flatten_obstacles against a literal restatement of datasets/load_test_dataset.py:105-151 on the
+    fields the reference reads off geometrout's Cuboid / Cylinder (center, wxyz quaternion, dims | radius, height)."""
+    from edmp_b200 import scene
+    rng = np.random.default_rng(0)
+    cuboids = [(rng.normal(size=3), rng.normal(size=4), rng.uniform(0.1, 0.5, 3)) for _ in range(3)]
+    cylinders = [(rng.normal(size=3), rng.normal(size=4), rng.uniform(0.05, 0.2), rng.uniform(0.1, 0.6)) for _ in range(2)]
+    cfg, cub, cyl, nb, nc = scene.flatten_obstacles(cuboids, cylinders)
+    assert (nb, nc) == (3, 2) and cfg.shape == (5, 10) and cub.shape == (3, 10) and cyl.shape == (2, 9)
+    # the reference's steps, one by one
+    c_cent = np.array([c for c, _, _ in cuboids]); c_dims = np.array([d for _, _, d in cuboids])
+    c_quat = np.roll(np.array([q for _, q, _ in cuboids]), -1, axis=1)                       # :128
+    y_cent = np.array([c for c, _, _, _ in cylinders])
+    y_quat = np.roll(np.array([q for _, q, _, _ in cylinders]), -1, axis=1)                  # :135
+    y_r = np.array([[r] for _, _, r, _ in cylinders]); y_h = np.array([[h] for _, _, _, h in cylinders])
+    y_dims = np.concatenate([y_r, y_r, y_h], axis=1)                                         # :136-139
+    want = np.concatenate([np.concatenate([c_cent, y_cent]), np.concatenate([c_quat, y_quat]),
+                           np.concatenate([c_dims, y_dims])], axis=1)                        # :141-151
+    np.testing.assert_array_equal(cfg, want)
+    np.testing.assert_array_equal(cub, np.concatenate([c_cent, c_quat, c_dims], axis=1))     # :129
+    np.testing.assert_array_equal(cyl, np.concatenate([y_cent, y_quat, y_r, y_h], axis=1))   # :136
+    # cuboids only / cylinders only / empty
+    only_b = scene.flatten_obstacles(cuboids, ())
+    assert only_b[0].shape == (3, 10) and only_b[2].shape == (0, 9) and only_b[4] == 0
+    only_c = scene.flatten_obstacles((), cylinders)
+    assert only_c[0].shape == (2, 10) and only_c[3] == 0
+    with pytest.raises(ValueError):
+        scene.flatten_obstacles((), ())
+
+
+def test_goal_selection_like_the_entry_point():
+    """edmp_b200.scene.select_goal: infer_serial.py:122-129 (volume trust region, then joint-space distance)."""
+    from edmp_b200 import scene
+    start = np.zeros(7)
+    goals = np.stack([np.full(7, 3.0), np.full(7, 1.0), np.full(7, 0.5), np.full(7, 2.0)])
+    vol = np.array([0.0, 0.0005, 0.01, 0.0007999])
+    goal, idx = scene.select_goal(vol, start, goals)
+    assert idx == 1 and np.array_equal(goal, goals[1])        # 2 is nearest but outside the trust region
+    goal, idx = scene.select_goal(vol, start, goals, trust_region=0.02)
+    assert idx == 2
+    goal, idx = scene.select_goal(np.array([0.3]), start, goals[:1])
+    assert idx == 0
+    with pytest.raises(ValueError):
+        scene.select_goal(vol[:2], start, goals)
