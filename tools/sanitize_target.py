@@ -36,3 +36,11 @@ c, gr, cl = g.evaluate(q)
 cc = g.cloud_clearance(np.random.default_rng(0).uniform(-0.5, 0.9, size=(1500, 3)), q)
 torch.cuda.synchronize()
 print("sdf ok", float(c.sum()), float(cc.min()))
+from edmp_b200.lib import MetricsCalculator  # noqa: E402
+mc = MetricsCalculator(guide)
+traj = np.cumsum(np.random.default_rng(1).normal(scale=0.03, size=(37, 7, 50)), axis=2)
+r = mc.ensemble_metrics(traj, 0.04, return_spectra=True)
+s = mc.sparc(np.exp(-5 * np.arange(-1, 1, 0.01) ** 2), fs=100.)
+T = guide.get_end_effector_transform(guide.rearrange_joints(torch.tensor(traj, dtype=torch.float32, device=dev)))
+torch.cuda.synchronize()
+print("metrics ok", float(r["joint_smoothness"].mean()), s[0], tuple(T.shape))
