@@ -20,6 +20,10 @@ bool pdl_enabled() {
   static const bool on = std::getenv("EDMP_NO_PDL") == nullptr;
   return on;
 }
+bool cluster_pdl_enabled() {
+  static const bool on = std::getenv("EDMP_NO_PAIR_PDL") == nullptr;
+  return on;
+}
 }  // namespace edmp
 
 using namespace edmp;

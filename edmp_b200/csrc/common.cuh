@@ -41,6 +41,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();
+bool cluster_pdl_enabled();   // EDMP_NO_PAIR_PDL=1 switches it off (A/B)
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -66,13 +67,17 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster_x;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch for the cluster kernels as well: without it a CTA-pair layer starts only after the
+  // previous kernel has drained grid-wide, and the row-tile chaining of consecutive layers never comes into play
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = (pdl_enabled() && cluster_pdl_enabled()) ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
