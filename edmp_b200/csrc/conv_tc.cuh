@@ -101,10 +101,18 @@ template <> struct TcElem<TC_EL_TF32> {
   static constexpr int kUnitChunks = 4;  // 16-byte chunks that 16 channels occupy
 };
 
-// byte offset of 16-byte chunk `chunk16` of row `row_local` inside a tiled block
+// Byte offset of 16-byte chunk `chunk16` (0..7) of row `row_local` inside a tiled activation block.  Blocks are CHUNK-MAJOR
+// [chunk][128 rows][16 B] -- the un-swizzled ("interleaved") K-major UMMA layout, core matrix = 8 rows x 16 B -- so that
+// an epilogue warp (a thread = a row) touches 512 contiguous bytes per 16-byte store / residual load instead of 32
+// different 128-byte lines as with row-major SWIZZLE_128B rows (the L1 tag stage, one line per cycle, was what made the
+// identity-residual loads cost +10k cycles per tile).  Weight tiles keep SWIZZLE_128B.
+constexpr int kTcChunkStride = kTcRows * 16;   // bytes between consecutive 16-byte K chunks of a block (UMMA LBO)
 __device__ __forceinline__ int tc_swz_bytes(int row_local, int chunk16) {
-  return row_local * 128 + ((chunk16 ^ (row_local & 7)) << 4);
+  return chunk16 * kTcChunkStride + row_local * 16;
 }
+// UMMA descriptor of a tiled activation block in shared memory (without the start address)
+__device__ __forceinline__ uint64_t tc_act_desc0() { return umma::make_desc_interleaved(0, kTcChunkStride, 128); }
+constexpr int kTcActKStep = (2 * kTcChunkStride) >> 4;   // descriptor start-address increment per 32-byte K step
 
 // swizzle of 16-byte chunk `c` in row `r` of a position-major atom with `rby`-byte rows (32 / 64 / 128)
 __device__ __forceinline__ int pm_swz(int rby, int r, int c) {
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           umma::tc_fence_after();
           if (dbg && a_it == 0 && lane == 0) dbg[3] = clock64();
           const uint32_t a_base = umma::smem_u32(a_smem + as * a_stage_bytes);
-          const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
-          const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+          const uint64_t da_hi = tc_act_desc0() | (uint64_t)((a_base & 0x3FFFF) >> 4);
+          const uint64_t da_lo = tc_act_desc0() | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
           // first K chunk: the window's positions may differ in "already written", so issue one
           // MMA per position with its own accumulate flag; afterwards one windowed MMA.
           const int n_issue = (cc == 0) ? s.n_slots : 1;
@@ -363,19 +371,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 const uint32_t acc = acc0 | (uint32_t)(ks > 0);
                 if (BF16) {
                   if (a.split) {
-                    umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                    umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                    umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                    umma::mma_bf16(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                    umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                    umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
                   } else {
-                    umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                    umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                   }
                 } else {
                   if (a.split) {
-                    umma::mma_tf32(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                    umma::mma_tf32(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                    umma::mma_tf32(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                    umma::mma_tf32(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                    umma::mma_tf32(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
                   } else {
-                    umma::mma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                    umma::mma_tf32(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                   }
                 }
               }

@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       // tensor pipe's critical path (profiles/micro/r1_mma_pipe.txt).  A token (named barrier + tcgen05 fences)
       // keeps the issue order identical to the single-warp order. =====
       const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
-      const uint64_t desc0 = umma::make_desc_sw128(0);
+      const uint64_t desc0 = umma::make_desc_sw128(0);     // weight tiles: SWIZZLE_128B rows
+      const uint64_t desc_a0 = tc_act_desc0();             // activation blocks: chunk-major, no swizzle (conv_tc.cuh)
       uint32_t buf = 0, eph = 0;   // accumulator buffer and the parity of its "empty" barrier
       uint32_t step = 0;
       long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0;
@@ -387,8 +388,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                   if (dbg) w_a += clock64() - tw;
                 }
                 const uint32_t a_base = a0 + as * (uint32_t)a_stage_bytes;
-                const uint64_t da_hi = desc0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
-                const uint64_t da_lo = desc0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+                const uint64_t da_hi = desc_a0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+                const uint64_t da_lo = desc_a0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
                 // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are
                 // written for the first time -> two runs with their own accumulate flag; afterwards one run
                 const int n_first = (cc == 0) ? s.n_acc : s.n_slots;
@@ -411,19 +412,19 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                       const uint32_t acc = accf | (uint32_t)(ks > 0);
                       if (CG == 2) {
                         if (a.split) {
-                          t2::mma_f16_cg2(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                          t2::mma_f16_cg2(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                          t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                          t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
                         } else {
-                          t2::mma_f16_cg2(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                          t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                         }
                       } else {
                         if (a.split) {
-                          umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                          umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                          umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                          umma::mma_bf16(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                          umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                          umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
                         } else {
-                          umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                          umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                         }
                       }
                     }

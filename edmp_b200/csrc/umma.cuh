@@ -96,6 +96,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major operand tile WITHOUT swizzle ("interleaved": 8-row x 16-byte core matrices of 128 contiguous bytes); lbo = byte
+// distance between the two core matrices of one 32-byte K step, sbo = byte distance between 8-row groups.
+// layout type SWIZZLE_NONE (0)
+__device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // kind::tf32 / kind::f16 instruction descriptor: D = F32, A/B format, both K-major, M x N.
 // fmt: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16), 0 = F16
 __device__ __forceinline__ uint32_t make_idesc(int fmt, int M, int N) {
