@@ -7,10 +7,13 @@
 //   * a CTA owns a block of 8 trajectory rows and ALL positions of a layer;
 //   * MMA lane m of M tile mt  <->  output index 16*mt + m/8, trajectory row m%8;
 //   * activations live in HBM as ready-made UMMA shared-memory images in "position-major" order:
-//       [row block][padded position p = l + 2, 0 .. L+3][8 rows][C halves]   (hi part and lo part)
-//     one swizzle atom (8 rows x 2C bytes, C = 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B) per position,
-//     positions -2,-1,L,L+1 are zero (the convolution's zero padding).  Neighbouring positions are
-//     exactly one atom apart, so
+//       [row block][16-byte channel chunk][padded position p = l + 2, 0 .. L+3][8 rows][16 B]   (hi part and lo part)
+//     -- the un-swizzled K-major UMMA layout (core matrix = the 8 rows of one position, LBO = (L + 4) * 128 B between
+//     chunks, SBO = 128 B between positions; conv_tc.cuh pm_act_off); earlier it was one swizzle atom
+//     (8 rows x 2C bytes) per position, which made every epilogue store touch 32 separate lines.  Weight images keep
+//     the swizzled atoms (8 rows x 2C bytes, C = 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B).
+//     Positions -2,-1,L,L+1 are zero (the convolution's zero padding).  Neighbouring positions are
+//     exactly 128 B apart, so
 //       - a filter tap is a START-ADDRESS offset of the A descriptor (no im2col, no data movement),
 //       - the stride-2 of nn.Conv1d(k=3,s=2,p=1) is a doubled STRIDE-BYTE-OFFSET,
 //       - nn.ConvTranspose1d(k=4,s=2,p=1) is two interleaved 2-tap convolutions (even / odd outputs);
@@ -207,20 +210,23 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
         const PmTerm t = a.terms[ti];
         const uint32_t d = tmem_base + (uint32_t)((t.acc * ntiles + mt) * COUT);
         for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
+          const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * 128);
           const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
-          const uint64_t da_hi = pm_desc(a_addr, a.stride * atom, rby), da_lo = pm_desc(a_addr + a_lo_off, a.stride * atom, rby);
+          const uint32_t lbo = (uint32_t)(a.lin + 4) * 128u;
+          const uint64_t da_hi = umma::make_desc_interleaved(a_addr, lbo, a.stride * 128),
+                         da_lo = umma::make_desc_interleaved(a_addr + a_lo_off, lbo, a.stride * 128);
           const uint64_t db_hi = pm_desc(w_addr, atom, rby), db_lo = pm_desc(w_addr + w_lo_off, atom, rby);
           const uint32_t acc0 = (touched >> t.acc) & 1u;
           if (umma::elect_one()) {
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t acc = acc0 | (uint32_t)(ks > 0);
               if (a.split) {
-                umma::mma_bf16(d, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-                umma::mma_bf16(d, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-                umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+                const uint32_t ka = (uint32_t)ks * (lbo >> 3);   // two 16-byte chunks per K step, in 16-byte units
+                umma::mma_bf16(d, da_lo + ka, db_hi + 2 * ks, idesc, acc);
+                umma::mma_bf16(d, da_hi + ka, db_lo + 2 * ks, idesc, 1u);
+                umma::mma_bf16(d, da_hi + ka, db_hi + 2 * ks, idesc, 1u);
               } else {
-                umma::mma_bf16(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+                umma::mma_bf16(d, da_hi + (uint32_t)ks * (lbo >> 3), db_hi + 2 * ks, idesc, acc);
               }
             }
           }
@@ -296,7 +302,6 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
 
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const int n_acc = a.n_groups + a.aux;
-    const int rby_o = 2 * a.cout;               // output line bytes (full channel count of the layer)
     const int chunk0 = c0 >> 3;                 // first 16-byte chunk of this CTA's channels in a line
     for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
       const bool is_aux = a.aux && g_acc == a.n_groups;
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
         const int idx = 16 * mt + pos_in_tile;
         const bool valid = idx < a.n_m && grow < a.rows;
         const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
-        const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
+        const size_t img = (size_t)rb * pm_img_bytes(a.lout, a.cout);                   // this row block's image
         float fin[7];
 #pragma unroll
         for (int j = 0; j < 7; ++j) fin[j] = 0.0f;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
             // out + x (blocks.py:164, identity residual): x = hi + lo of the block input, same layout
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-              const size_t off = line + (size_t)(pm_swz(rby_o, row, chunk0 + 2 * u + m) << 4);
+              const size_t off = img + pm_act_off(a.lout, lo, row, chunk0 + 2 * u + m);
               const uint4 h = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
               uint4 l = make_uint4(0, 0, 0, 0);
               if (a.res.lo) l = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
             if (o_hi) {
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
-                const size_t off = line + (size_t)(pm_swz(rby_o, row, chunk0 + 2 * u + m) << 4);
+                const size_t off = img + pm_act_off(a.lout, lo, row, chunk0 + 2 * u + m);
                 *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
                 if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
               }
@@ -414,10 +419,9 @@ __global__ void pm_pack_input_kernel(const float* __restrict__ x, int rows, int 
   uint4 h[4], r[4];
   tc_split_store<EL>(v, lo != nullptr, h, r);
   const int rb = row / kPmRows, rr = row % kPmRows;
-  const size_t line = ((size_t)(rb * (L + 4) + l + 2) * 8 + rr) * 32;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
-    const size_t off = line + (size_t)(pm_swz(32, rr, m) << 4);
+    const size_t off = (size_t)rb * pm_img_bytes(L, 16) + pm_act_off(L, l, rr, m);
     *reinterpret_cast<uint4*>((uint8_t*)hi + off) = h[m];
     if (lo) *reinterpret_cast<uint4*>((uint8_t*)lo + off) = r[m];
   }
@@ -430,8 +434,8 @@ __global__ void pm_unpack_kernel(const void* __restrict__ hi, const void* __rest
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * C * L) return;
   const int l = (int)(i % L), c = (int)((i / L) % C), row = (int)(i / ((size_t)C * L));
-  const int rb = row / kPmRows, rr = row % kPmRows, rby = 2 * C;
-  const size_t off = ((size_t)(rb * (L + 4) + l + 2) * 8 + rr) * rby + (size_t)(pm_swz(rby, rr, c >> 3) << 4) + (c & 7) * 2;
+  const int rb = row / kPmRows, rr = row % kPmRows;
+  const size_t off = (size_t)rb * pm_img_bytes(L, C) + pm_act_off(L, l, rr, c >> 3) + (c & 7) * 2;
   float v = unpack16x2<EL>((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)hi + off)).x;
   if (lo) v += unpack16x2<EL>((uint32_t)*reinterpret_cast<const uint16_t*>((const uint8_t*)lo + off)).x;
   x[i] = v;

@@ -82,11 +82,12 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       const PmTerm t = a.terms[ti];
       uint32_t seen = 0;
       for (int tj = 0; tj < ti; ++tj) seen |= (a.terms[tj].acc == t.acc) ? 1u : 0u;
-      const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * atom);
+      const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * 128);
       const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
+      const uint32_t lbo = (uint32_t)(a.lin + 4) * 128u, ka = (uint32_t)ks * (lbo >> 3);   // K step = two 16-byte chunks
       PmIssue it;
-      it.da_hi = (uint32_t)(pm_desc(a_addr, a.stride * atom, rby) + 2 * ks);
-      it.da_lo = (uint32_t)(pm_desc(a_addr + (uint32_t)(nkc * a.a_bytes_img), a.stride * atom, rby) + 2 * ks);
+      it.da_hi = (uint32_t)(umma::make_desc_interleaved(a_addr, lbo, a.stride * 128) + ka);
+      it.da_lo = (uint32_t)(umma::make_desc_interleaved(a_addr + (uint32_t)(nkc * a.a_bytes_img), lbo, a.stride * 128) + ka);
       it.db_hi = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);
       it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)a.w_bytes_part, atom, rby) + 2 * ks);
       it.d_off = (uint32_t)((t.acc * ntiles + mt) * COUT);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     umma::mbar_wait(&bar_w, 0);
     const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
     const int n_issue = ntiles * a.n_terms * nkc * (C >> 4);
-    const uint64_t hi_a = pm_desc(0, a.stride * atom, rby) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
+    const uint64_t hi_a = umma::make_desc_interleaved(0, 0, a.stride * 128) & 0xFFFFFFFF00000000ull;   // SBO, version, no swizzle
     const uint64_t hi_b = pm_desc(0, atom, rby) & 0xFFFFFFFF00000000ull;
     uint32_t ph = 0, k = 0;
     long long w_acc = 0, w_a = 0, t_begin = dbg ? clock64() : 0;
@@ -254,7 +255,6 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
 
       if (dbg) t_stats += clock64() - t_start;
       const int n_acc = a.n_groups + a.aux;
-      const int rby_o = 2 * a.cout;               // output line bytes
       for (int g_acc = 0; g_acc < n_acc; ++g_acc) {
         const bool is_aux = a.aux && g_acc == a.n_groups;
         const bool gn = !is_aux && a.mode != PM_BIAS;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
           const int idx = 16 * mt + pos_in_tile;
           const bool valid = idx < a.n_m && grow < a.rows;
           const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
-          const size_t line = ((size_t)(rb * (a.lout + 4) + lo + 2) * 8 + row) * rby_o;   // byte offset of (p, r)
+          const size_t img = (size_t)rb * pm_img_bytes(a.lout, a.cout);                   // this row block's image
           f2::f32x2 fin2[7];
 #pragma unroll
           for (int j = 0; j < 7; ++j) fin2[j] = f2::dup(0.0f);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
             if (res) {
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
-                const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
+                const size_t off = img + pm_act_off(a.lout, lo, row, 2 * u + m);
                 rh[m] = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
                 rl[m] = a.res.lo ? *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off) : make_uint4(0, 0, 0, 0);
               }
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
               if (o_hi) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                  const size_t off = line + (size_t)(pm_swz(rby_o, row, 2 * u + m) << 4);
+                  const size_t off = img + pm_act_off(a.lout, lo, row, 2 * u + m);
                   *reinterpret_cast<uint4*>((uint8_t*)o_hi + off) = h[m];
                   if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
                 }

@@ -114,7 +114,17 @@ __device__ __forceinline__ int tc_swz_bytes(int row_local, int chunk16) {
 __device__ __forceinline__ uint64_t tc_act_desc0() { return umma::make_desc_interleaved(0, kTcChunkStride, 128); }
 constexpr int kTcActKStep = (2 * kTcChunkStride) >> 4;   // descriptor start-address increment per 32-byte K step
 
-// swizzle of 16-byte chunk `c` in row `r` of a position-major atom with `rby`-byte rows (32 / 64 / 128)
+// Position-major ACTIVATION images (conv_pm*.cuh) are chunk-major like the tiled blocks above: per block of 8 trajectory
+// rows [16-byte chunk][position -2 .. L+1][8 rows][16 B] -- the un-swizzled K-major UMMA layout whose core matrix is the
+// 8 rows of one position; LBO = (L + 4) * 128 B (next chunk), SBO = 128 B (next position; doubled for a stride-2 conv),
+// a filter tap = a start-address offset of 128 B.  An epilogue warp (4 positions x 8 rows) then writes 512 contiguous
+// bytes per 16-byte store instead of 32 separate lines.  pm_act_off: byte offset of (position p, row r, chunk) in an image.
+__device__ __forceinline__ size_t pm_act_off(int L, int p, int r, int chunk) {
+  return ((size_t)chunk * (L + 4) + (size_t)(p + 2)) * 128 + (size_t)r * 16;
+}
+__device__ __forceinline__ size_t pm_img_bytes(int L, int C) { return (size_t)(L + 4) * 16 * C; }   // hi (or lo) part of one row block
+
+// swizzle of 16-byte chunk `c` in row `r` of a position-major WEIGHT atom with `rby`-byte rows (32 / 64 / 128)
 __device__ __forceinline__ int pm_swz(int rby, int r, int c) {
   return rby == 128 ? (c ^ (r & 7)) : (rby == 64 ? (c ^ ((r >> 1) & 3)) : (c ^ ((r >> 2) & 1)));
 }
@@ -584,10 +594,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           size_t dst = ((size_t)rt * (a.lout * kch_out) + (k >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(r, chunk);
           if (BF16 && a.out_pm) {
             // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
-            const int grow = rt * kTcRows + r, rby = 2 * a.cout;
+            const int grow = rt * kTcRows + r;
             const int c = nt * a.ct + (u * 16) % a.ct;
-            dst = ((size_t)((grow >> 3) * (a.lout + 4) + lo + 2) * 8 + (grow & 7)) * rby +
-                  (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
+            dst = (size_t)(grow >> 3) * pm_img_bytes(a.lout, a.cout) + pm_act_off(a.lout, lo, grow & 7, (c >> 3) + m);
           }
           const int sw = (UC == 4) ? ((r >> 1) & 3) : ((r >> 2) & 1);
           const size_t src = ((size_t)(uu * 128 + r) * UC + (m ^ sw)) * 16;

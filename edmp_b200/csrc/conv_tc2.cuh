@@ -735,9 +735,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 size_t dst;
                 if (a.out_pm) {
                   // hand-over to the position-major levels: [row block of 8][lo + 2][8 rows][cout halves]
-                  const int rby = 2 * a.cout, c = nt * ct + c0;
-                  dst = ((size_t)((grow >> 3) * (L + 4) + lo + 2) * 8 + (grow & 7)) * rby +
-                        (size_t)(pm_swz(rby, grow & 7, (c >> 3) + m) << 4);
+                  const int c = nt * ct + c0;
+                  dst = (size_t)(grow >> 3) * pm_img_bytes(L, a.cout) + pm_act_off(L, lo, grow & 7, (c >> 3) + m);
                 } else {
                   dst = ((size_t)rt * (L * kch_out) + (kk >> E::kShift)) * kTcBlockBytes + tc_swz_bytes(row_local, chunk + m);
                 }
