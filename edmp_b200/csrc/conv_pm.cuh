@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
                 if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
               }
             } else {
-              // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
+              // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][8 chunks][128 rows x 16 B] (tc_swz_bytes)
               const int rt = grow / kTcRows, rl = grow % kTcRows;
               const int k = lo * a.cout + c0 + u * 16;
               const size_t blk = ((size_t)rt * (a.lout * (a.cout >> 6)) + (k >> 6)) * kTcBlockBytes;

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
                   if (o_lo) *reinterpret_cast<uint4*>((uint8_t*)o_lo + off) = l[m];
                 }
               } else {
-                // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][128 rows x 128 B], SWIZZLE_128B
+                // rows-as-M tiles of conv_tc.cuh: [row tile][l][c chunk of 64][8 chunks][128 rows x 16 B] (tc_swz_bytes)
                 const int rt = grow / kTcRows, rl_ = grow % kTcRows;
                 const int kk = lo * a.cout + u * 16;
                 const size_t blk = ((size_t)rt * (a.lout * (a.cout >> 6)) + (kk >> 6)) * kTcBlockBytes;

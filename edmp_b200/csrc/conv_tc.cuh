@@ -9,9 +9,9 @@
 //     output positions within the filter's reach, i.e. a contiguous column window of the
 //     accumulator, so each chunk is ONE windowed tcgen05.mma (N_w = #positions x channels) and no
 //     zero-padding tap is ever multiplied (exactly the non-padding MACs);
-//   * operands are pre-tiled in global memory as ready-made UMMA shared-memory images
-//     (128 rows x 128 B, SWIZZLE_128B, K-major): producer threads move them with 1-D bulk async
-//     copies (TMA engine) signalled on mbarriers -- no tensor maps needed;
+//   * operands are pre-tiled in global memory as ready-made UMMA shared-memory images (K-major; weight tiles 128-byte
+//     rows with SWIZZLE_128B, activation blocks 128 rows x 128 B chunk-major without swizzle, see tc_swz_bytes below):
+//     producer threads move them with 1-D bulk async copies (TMA engine) signalled on mbarriers -- no tensor maps;
 //   * fp32 fidelity: every operand exists as a "hi" part and a "lo" remainder (TF32 or BF16) and
 //     each product is three MMAs (lo*hi + hi*lo + hi*hi): "3xTF32" (~2^-22 operand error) or
 //     "3xBF16" (~2^-17).  The single-pass modes use the hi part only;
