@@ -115,6 +115,21 @@ def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, monkeypatch):
         assert np.abs(eps - ref).max() <= EPS_TOL[prec]
 
 
+@pytest.mark.parametrize("env", ["EDMP_PM_V1", "EDMP_TC_V1", "EDMP_NO_CHAIN"])
+def test_unet_fallback_kernel_generations_match_oracle(tmp_path_factory, sd, env, monkeypatch):
+    """The first-generation kernels (conv_pm / conv_tc, selected by EDMP_PM_V1 / EDMP_TC_V1) and the un-chained launch order
+    read and write the same activation layouts as the default path: they must keep matching the oracle."""
+    if "f16x3" not in PRECISIONS:
+        pytest.skip("f16x3 not selected")
+    monkeypatch.setenv(env, "1")
+    m = _model(tmp_path_factory, sd, "f16x3")
+    x = torch.randn(137, 7, 50, generator=torch.Generator().manual_seed(5)) * 1.5
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, x, 191).numpy()
+    eps = m(x.to(DEV), 191).cpu().numpy()
+    assert np.abs(eps - ref).max() <= EPS_TOL["f16x3"]
+
+
 def test_unet_headline_batch_matches_small_batch(tmp_path_factory, sd):
     """8190 rows (the bench workload: persistent tile walk, CTA pairs chosen automatically): rows spread over the
     batch equal the same rows run through a small engine, and against the oracle."""
