@@ -200,3 +200,26 @@ def test_committed_bench_line_has_the_contract_keys():
     ref = json.load(open(os.path.join(ROOT, "profiles", "r1_final_reference_arm_bench.json")))
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
+
+
+def test_metrics_nfft_matches_the_reference_formula():
+    """edmp_metrics_nfft is host-only arithmetic: int(2 ** (ceil(log2(m)) + padlevel)) of lib/metrics.py:90."""
+    from edmp_b200 import _lib
+    lib = _lib.load()
+    for m in (1, 2, 3, 48, 49, 63, 64, 65, 200, 1000):
+        for pad in (0, 2, 4):
+            assert lib.edmp_metrics_nfft(m, pad) == int(2 ** (np.ceil(np.log2(m)) + pad)), (m, pad)
+    assert lib.edmp_metrics_nfft(0, 4) == 0 and lib.edmp_metrics_nfft(49, -1) == 0
+
+
+def test_sparc_oracle_properties():
+    """Size-independent properties of the spectral arc length (oracle side): invariant to the amplitude of the profile
+    and to time reversal (the magnitude spectrum is), and smoother profiles score closer to zero."""
+    from oracle import metrics_oracle as mo
+    t = np.linspace(0, 1, 49)
+    bell = np.exp(-((t - 0.5) / 0.18) ** 2)
+    wobble = bell * (1 + 0.3 * np.sin(2 * np.pi * 6 * t))
+    a = mo.sparc(bell, 50.)[0]
+    np.testing.assert_allclose(mo.sparc(3.7 * bell, 50.)[0], a, rtol=1e-12)
+    np.testing.assert_allclose(mo.sparc((bell + 0.2 * t)[::-1], 50.)[0], mo.sparc(bell + 0.2 * t, 50.)[0], rtol=1e-9)
+    assert mo.sparc(wobble, 50.)[0] < a < 0
