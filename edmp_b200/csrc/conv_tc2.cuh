@@ -74,6 +74,10 @@ struct Tc2Args {
   int dep_target;
   int* done;
   int b_pad;                      // 1: weight stages are [zero slot][real slots][zero slot], neighbouring stages share a zero slot
+  // Column split of a GroupNorm group over a thread-block cluster (small batches: more, narrower tiles so that one wave
+  // covers the machine): ct = cg / nsplit, the nsplit CTAs of a cluster hold the column tiles of ONE group of the same row
+  // tile and exchange their partial (mean, M2) through distributed shared memory.  1: no cluster.
+  int nsplit;
   int n_row_tiles, n_col_tiles;   // n_row_tiles counts 128-row tiles (even for CG = 2)
   int ct_log2, cg_log2, nct_log2; // ct, cg and n_col_tiles are powers of two
   const float *bias, *gamma, *beta, *temb, *bres;
@@ -112,6 +116,26 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(umma::smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// store one float into the shared memory of CTA `rank` of the cluster (same offset as `p` has here)
+__device__ __forceinline__ void st_remote_f32(float* p, uint32_t rank, float v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(umma::smem_u32(p)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+// wait on a local barrier that CTAs of the cluster arrive on (acquire at cluster scope: their remote stores are visible)
+__device__ __forceinline__ void wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(umma::smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
+  }
 }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread, WITHOUT waiting: several loads can be in
 // flight before one tmem_ld_wait()
@@ -177,11 +201,14 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   __shared__ uint64_t a_full[kT2MaxAStages], a_empty[kT2MaxAStages], b_full[kT2MaxBStages], b_empty[kT2MaxBStages];
   __shared__ uint64_t pa_full[kT2MaxAStages], pb_full[kT2MaxBStages];   // CG = 2, leader: "the peer's stage is full"
   __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t xg_full[2];   // nsplit > 1: "the partial group statistics of every cluster peer have arrived" (by tile parity)
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_par2[2][5 * 128];        // bias | gamma | beta | temb | bres of a column tile (by tile parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? t2::cluster_ctarank() : 0u;
+  const uint32_t nsplit = CG == 1 ? (uint32_t)a.nsplit : 1u;               // column split of a GroupNorm group over a cluster
+  const uint32_t crank = nsplit > 1 ? t2::cluster_ctarank() : 0u;
   const int nparts = a.split ? 2 : 1;
   const int a_stage_bytes = kTcBlockBytes * nparts;
   int max_slots = a.ph[0].slots;
@@ -213,6 +240,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     // (with two issuing warps each commits the weight stage / the accumulator after its own last step)
     for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, a.mma_warps); umma::mbar_init(pb_full + i, 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, a.mma_warps); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
+    for (int i = 0; i < 2; ++i) umma::mbar_init(xg_full + i, nsplit > 1 ? (nsplit - 1) * 4 : 1);   // one arrive per peer and lane quarter
     umma::fence_barrier_init();
   }
   if (warp == 1) {
@@ -234,7 +262,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (CG == 2) t2::cluster_sync_all();
+  if (CG == 2 || nsplit > 1) t2::cluster_sync_all();
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   // everything above overlapped the previous kernel; activations are read below.  Chained layers synchronise per row
@@ -469,8 +497,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
     const int n_pieces_alloc = n_units * (two ? 2 : 1);
     float* my_stat = my_part + n_pieces_alloc * 256;   // [group][mean | rstd][128 rows]
-    const int n_groups = two ? (ct >> 3) : (ct >> cg_log2);
-    const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (cg >> 4)));
+    const int gw = min(cg, ct);                           // channels of a group inside this column tile (ct < cg: column split)
+    const int n_groups = two ? (ct >> 3) : max(1, ct >> cg_log2);
+    const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (gw >> 4)));
+    float* s_xg = my_part + (n_pieces_alloc + n_groups) * 256;   // nsplit > 1: [tile parity][source rank][mean | M2][128 rows]
+    uint32_t xg_par = 0, xg_ph = 0;
     uint32_t buf = 0, fph = 0;
     long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
     int tile_par = 0;
@@ -581,7 +612,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             }
             pstep = ch >> 4; npiece = 16.0f;
           } else {
-            p0[0] = (g << cg_log2) >> 4; cnt[0] = cg >> 4; pstep = ct >> 4; npiece = 16.0f;
+            p0[0] = ((g << cg_log2) & (ct - 1)) >> 4; cnt[0] = gw >> 4; pstep = ct >> 4; npiece = 16.0f;
           }
           // (four independent shared-memory loads per step: the serial load -> add chain over 13..16 pieces was 10-19 %
           // of the horizon 7 / 13 epilogues; cnt is a power of two)
@@ -616,9 +647,38 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             }
           }
           const float sq = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]), sd = (sd4[0] + sd4[1]) + (sd4[2] + sd4[3]);
-          my_stat[g * 256] = mu;
-          my_stat[g * 256 + 128] = rsqrtf(fmaf(npiece, sd, sq) * inv_n + 1e-5f);
+          float mean = mu, m2 = fmaf(npiece, sd, sq);
+          if (nsplit > 1) {
+            // this tile holds ct of the group's cg channels: exchange (mean, M2) with the cluster peers that hold the rest
+            // (same row tile, neighbouring column tiles, same walk step) and combine in rank order, so that every CTA of
+            // the cluster gets bit-identical statistics.  Only part 0 comes here (one group per tile): a warp per lane quarter.
+            float* xg = s_xg + xg_par * (4 * 256);
+            for (uint32_t pr = 0; pr < nsplit; ++pr)
+              if (pr != crank) {
+                t2::st_remote_f32(xg + crank * 256, pr, mean);
+                t2::st_remote_f32(xg + crank * 256 + 128, pr, m2);
+              }
+            __syncwarp();
+            if (lane == 0)
+              for (uint32_t pr = 0; pr < nsplit; ++pr)
+                if (pr != crank) t2::mbar_arrive_remote(xg_full + xg_par, pr);
+            t2::wait_cluster(xg_full + xg_par, xg_ph);
+            float ms[4], qs[4], msum = 0.0f;
+            for (uint32_t pr = 0; pr < nsplit; ++pr) {
+              ms[pr] = pr == crank ? mean : xg[pr * 256];
+              qs[pr] = pr == crank ? m2 : xg[pr * 256 + 128];
+              msum += ms[pr];
+            }
+            const float mall = msum / (float)nsplit;
+            float qall = 0.0f, dall = 0.0f;
+            for (uint32_t pr = 0; pr < nsplit; ++pr) { const float d = ms[pr] - mall; qall += qs[pr]; dall = fmaf(d, d, dall); }
+            mean = mall;
+            m2 = fmaf((float)(gw * L), dall, qall);
+          }
+          my_stat[g * 256] = mean;
+          my_stat[g * 256 + 128] = rsqrtf(m2 * inv_n + 1e-5f);
         }
+        if (nsplit > 1) { xg_par ^= 1; if (xg_par == 0) xg_ph ^= 1; }
         t2::bar_quarter(quarter);
         if (dbg) t_bar += clock64() - tb0;
       }
@@ -767,7 +827,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     umma::tc_fence_before();
   }
   __syncthreads();
-  if (CG == 2) t2::cluster_sync_all();
+  if (CG == 2 || nsplit > 1) t2::cluster_sync_all();   // (no CTA leaves while a peer may still write its shared memory)
   if (warp == 1) {
     umma::tc_fence_after();
     if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));

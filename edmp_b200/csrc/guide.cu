@@ -7,7 +7,9 @@
 // obstacle boxes are staged once per CTA into shared memory.
 #include "common.cuh"
 #include "guide.h"
+#include "philox.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -255,6 +257,68 @@ struct EndPoints {
   float start[7], goal[7];
 };
 
+// Gradient of one interior waypoint w: g[j] = d cost / d q_j(w); xr = the row's [7][ld] float64 trajectory (global
+// or shared memory), obstacle boxes of the row staged in s_omin / s_omax.
+__device__ __forceinline__ void waypoint_gradient(const double* __restrict__ xr, int ld, int off, int n_inner, bool clip,
+                                                  const EndPoints& ep, int w, bool sv, int n_obs,
+                                                  const float* s_omin, const float* s_omax, const float* s_half,
+                                                  float g[7]) {
+  float q[7], T[7][12];
+  load_waypoint(xr, ld, off, w, n_inner, ep.start, ep.goal, clip, q);
+  fk_frames(q, T);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) g[j] = 0.0f;
+  float Tp[7][12], Tn[7][12];
+  if (sv) {
+    float qq[7];
+    load_waypoint(xr, ld, off, w - 1, n_inner, ep.start, ep.goal, clip, qq);
+    fk_frames(qq, Tp);
+    load_waypoint(xr, ld, off, w + 1, n_inner, ep.start, ep.goal, clip, qq);
+    fk_frames(qq, Tn);
+  }
+  for (int l = 0; l < 9; ++l) {
+    Box b;
+    float pmin[3][3], pmax[3][3];
+    link_box<true>(T, l, s_half, b, pmin, pmax);
+    float cmax[3], cmin[3];
+    if (!sv) {
+      face_coefficients(b, n_obs, s_omin, s_omax, cmax, cmin);
+    } else {
+      Box bp, bn, u;
+      link_box<false>(Tp, l, s_half, bp, nullptr, nullptr);
+      link_box<false>(Tn, l, s_half, bn, nullptr, nullptr);
+      float amax[3], amin[3], bmax_[3], bmin_[3];
+      // segment (w, w+1)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(b.mn[k], bn.mn[k]); u.mx[k] = fmaxf(b.mx[k], bn.mx[k]); }
+      face_coefficients(u, n_obs, s_omin, s_omax, amax, amin);
+      // segment (w-1, w)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(bp.mn[k], b.mn[k]); u.mx[k] = fmaxf(bp.mx[k], b.mx[k]); }
+      face_coefficients(u, n_obs, s_omin, s_omax, bmax_, bmin_);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        cmax[k] = amax[k] * share_max(b.mx[k], bn.mx[k]) + bmax_[k] * share_max(b.mx[k], bp.mx[k]);
+        cmin[k] = amin[k] * share_min(b.mn[k], bn.mn[k]) + bmin_[k] * share_min(b.mn[k], bp.mn[k]);
+      }
+    }
+    // Jacobian pull: d p_k / d q_i = (z_i x (p - o_i))_k for joints i <= j(l)
+    const int jl = l < 6 ? l : 6;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (cmax[k] == 0.0f && cmin[k] == 0.0f) continue;
+      const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+      for (int i = 0; i <= jl; ++i) {
+        const float z1 = T[i][k1 * 4 + 2], z2 = T[i][k2 * 4 + 2];
+        const float o1 = T[i][k1 * 4 + 3], o2 = T[i][k2 * 4 + 3];
+        const float dmax = z1 * (pmax[k][k2] - o2) - z2 * (pmax[k][k1] - o1);
+        const float dmin = z1 * (pmin[k][k2] - o2) - z2 * (pmin[k][k1] - o1);
+        g[i] += cmax[k] * dmax - cmin[k] * dmin;
+      }
+    }
+  }
+}
+
 // ---- gradient: raw G (float32) + per-row sum of squares --------------------------------------
 // grid = rows, block = 64 (thread w < n_inner handles interior waypoint w)
 __global__ void __launch_bounds__(64) guide_grad_kernel(const SceneDev* __restrict__ sc,
@@ -280,59 +344,8 @@ __global__ void __launch_bounds__(64) guide_grad_kernel(const SceneDev* __restri
   const int n_obs = sc->n_obs;
   double sq = 0.0;
   if (w < n_inner) {
-    float q[7], T[7][12];
-    load_waypoint(xr, ld, off, w, n_inner, ep.start, ep.goal, clip, q);
-    fk_frames(q, T);
-    float g[7] = {0, 0, 0, 0, 0, 0, 0};
-    float Tp[7][12], Tn[7][12];
-    if (sv) {
-      float qq[7];
-      load_waypoint(xr, ld, off, w - 1, n_inner, ep.start, ep.goal, clip, qq);
-      fk_frames(qq, Tp);
-      load_waypoint(xr, ld, off, w + 1, n_inner, ep.start, ep.goal, clip, qq);
-      fk_frames(qq, Tn);
-    }
-    for (int l = 0; l < 9; ++l) {
-      Box b;
-      float pmin[3][3], pmax[3][3];
-      link_box<true>(T, l, s_half, b, pmin, pmax);
-      float cmax[3], cmin[3];
-      if (!sv) {
-        face_coefficients(b, n_obs, s_omin, s_omax, cmax, cmin);
-      } else {
-        Box bp, bn, u;
-        link_box<false>(Tp, l, s_half, bp, nullptr, nullptr);
-        link_box<false>(Tn, l, s_half, bn, nullptr, nullptr);
-        float amax[3], amin[3], bmax_[3], bmin_[3];
-        // segment (w, w+1)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(b.mn[k], bn.mn[k]); u.mx[k] = fmaxf(b.mx[k], bn.mx[k]); }
-        face_coefficients(u, n_obs, s_omin, s_omax, amax, amin);
-        // segment (w-1, w)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { u.mn[k] = fminf(bp.mn[k], b.mn[k]); u.mx[k] = fmaxf(bp.mx[k], b.mx[k]); }
-        face_coefficients(u, n_obs, s_omin, s_omax, bmax_, bmin_);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          cmax[k] = amax[k] * share_max(b.mx[k], bn.mx[k]) + bmax_[k] * share_max(b.mx[k], bp.mx[k]);
-          cmin[k] = amin[k] * share_min(b.mn[k], bn.mn[k]) + bmin_[k] * share_min(b.mn[k], bp.mn[k]);
-        }
-      }
-      // Jacobian pull: d p_k / d q_i = (z_i x (p - o_i))_k for joints i <= j(l)
-      const int jl = l < 6 ? l : 6;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (cmax[k] == 0.0f && cmin[k] == 0.0f) continue;
-        const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-        for (int i = 0; i <= jl; ++i) {
-          const float z1 = T[i][k1 * 4 + 2], z2 = T[i][k2 * 4 + 2];
-          const float o1 = T[i][k1 * 4 + 3], o2 = T[i][k2 * 4 + 3];
-          const float dmax = z1 * (pmax[k][k2] - o2) - z2 * (pmax[k][k1] - o1);
-          const float dmin = z1 * (pmin[k][k2] - o2) - z2 * (pmin[k][k1] - o1);
-          g[i] += cmax[k] * dmax - cmin[k] * dmin;
-        }
-      }
-    }
+    float g[7];
+    waypoint_gradient(xr, ld, off, n_inner, clip, ep, w, sv, n_obs, s_omin, s_omax, s_half, g);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       raw[((size_t)row * 7 + j) * n_inner + w] = g[j];
@@ -385,6 +398,134 @@ __global__ void __launch_bounds__(128) guide_apply_kernel(const float* __restric
       const double v = x[idx] - scale * mixed;
       x[idx] = v;
       xf[idx] = (float)v;
+    }
+  }
+}
+
+// ---- the whole per-step tail in ONE launch -----------------------------------------------------------
+// posterior update (diffusion.py:116-135) -> clip copy (:328) -> gradient (lib/guide.py:597-623) -> whole-ensemble norm
+// mix (:627-629) -> guided update (diffusion.py:341) -> endpoints (:347-349) -> float32 copy for the network.
+// A persistent grid (every CTA resident, a row per CTA and walk step, a thread per waypoint) in two phases around one
+// grid-wide barrier: the norm couples every row of an ensemble (and a zero norm poisons all of them with NaN like the
+// reference), so no row can be updated before every row's gradient exists.  Unguided steps are phase 1 only.
+struct TailArgs {
+  double* x; float* xf; const float* eps; const double* noise;
+  unsigned long long seed;
+  int t, ensemble_rows, rows, guided;
+  double c1, sqrt_alpha, beta;
+  double start[7], goal[7];
+  EndPoints ep;
+  const SceneDev* sc;
+  const double *clearance, *expansion, *schedule;
+  const unsigned char *method, *grad_norm;
+  float* raw; double* rowsq;
+  unsigned* bar; unsigned bar_target;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ TailArgs a) {
+  __shared__ float s_omin[kMaxObs * 3], s_omax[kMaxObs * 3];
+  __shared__ float s_half[27];
+  __shared__ double s_red[2];
+  __shared__ double s_x[kRowElems];
+  __shared__ float s_norm;
+  __shared__ int s_norm_ens;
+  constexpr int n_inner = kHorizon - 2;
+  // (guided steps release the next kernel only after the barrier: its CTAs must not take the place of CTAs of this
+  // grid that are not resident yet)
+  if (!a.guided) pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < 27 && a.guided) s_half[threadIdx.x] = a.sc->link_half[threadIdx.x / 3][threadIdx.x % 3];
+  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    // x_{t-1} = (x_t - c1 * eps) / sqrt(alpha) + beta * z; row 0 of an ensemble gets z = 0 at t == 1
+    for (int e = threadIdx.x; e < kRowElems; e += 64) {
+      const size_t i = (size_t)row * kRowElems + e;
+      const int j = e / kHorizon, l = e % kHorizon;
+      double z = a.noise ? a.noise[i] : philox_normal(a.seed, (uint32_t)a.t, i);
+      if (a.t == 1 && (row % a.ensemble_rows) == 0) z = 0.0;
+      double v = (a.x[i] - a.c1 * (double)a.eps[i]) / a.sqrt_alpha + a.beta * z;
+      if (l == 0) v = a.start[j];
+      if (l == kHorizon - 1) v = a.goal[j];
+      s_x[e] = v;
+      a.x[i] = v;
+      a.xf[i] = (float)v;
+    }
+    if (!a.guided) continue;
+    stage_obstacles(a.sc, true, a.expansion[(size_t)row * kTSteps + a.t - 1], a.clearance[(size_t)row * kTSteps + a.t - 1],
+                    s_omin, s_omax);
+    __syncthreads();
+    double sq = 0.0;
+    const int w = threadIdx.x;
+    if (w < n_inner) {
+      float g[7];
+      waypoint_gradient(s_x, kHorizon, 1, n_inner, true, a.ep, w, a.method[row] != 0, a.sc->n_obs, s_omin, s_omax, s_half, g);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        a.raw[((size_t)row * 7 + j) * n_inner + w] = g[j];
+        sq += (double)g[j] * (double)g[j];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+    __syncthreads();   // (also: every thread is done with s_x and the obstacle boxes of this row)
+    if (threadIdx.x == 0) a.rowsq[row] = s_red[0] + s_red[1];
+  }
+  if (!a.guided) return;
+
+  // ---- grid-wide barrier: every row's raw gradient and sum of squares is written ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(a.bar, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(a.bar) < a.bar_target) {
+      __nanosleep(64);
+      if (clock64() - t0 > (1ll << 32)) {   // ~2 s: a protocol bug traps instead of hanging the GPU
+        printf("edmp: step_tail grid barrier timed out (block %d: %u of %u)\n", blockIdx.x, ld_acquire_u32(a.bar), a.bar_target);
+        __trap();
+      }
+    }
+    s_norm_ens = -1;
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    const int ens = row / a.ensemble_rows;
+    if (ens != s_norm_ens) {
+      // Frobenius norm of the ensemble's whole gradient (lib/guide.py:629), summed in a fixed order
+      const double* rs = a.rowsq + (size_t)ens * a.ensemble_rows;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int r = threadIdx.x;
+      for (; r + 192 < a.ensemble_rows; r += 256) { s0 += rs[r]; s1 += rs[r + 64]; s2 += rs[r + 128]; s3 += rs[r + 192]; }
+      for (; r < a.ensemble_rows; r += 64) s0 += rs[r];
+      double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      __syncthreads();   // every thread has read s_norm_ens
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
+      __syncthreads();
+      if (threadIdx.x == 0) { s_norm = (float)sqrt(s_red[0] + s_red[1]); s_norm_ens = ens; }
+      __syncthreads();
+    }
+    const float norm = s_norm;  // np.linalg.norm of a float32 array is float32
+    const double gn = a.grad_norm[row] ? 1.0 : 0.0;
+    const double scale = a.schedule[(size_t)row * kTSteps + a.t - 1];
+    for (int e = threadIdx.x; e < 7 * n_inner; e += 64) {
+      const float G = a.raw[(size_t)row * 7 * n_inner + e];
+      // float32 division, float64 mix -- 0/0 = NaN poisons every row of the ensemble like the reference
+      const double mixed = (1.0 - gn) * (double)G + gn * (double)(G / norm);
+      const int j = e / n_inner, w = e % n_inner;
+      const size_t idx = (size_t)row * kRowElems + j * kHorizon + 1 + w;
+      const double v = a.x[idx] - scale * mixed;
+      a.x[idx] = v;
+      a.xf[idx] = (float)v;
     }
   }
 }
@@ -606,6 +747,41 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
   if (raw_out)
     EDMP_CK(cudaMemcpyAsync(raw_out, s->raw, (size_t)rows * 7 * n_inner * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// One launch per reverse step after the UNet (see step_tail_kernel).  bar: a device counter zeroed by the caller at the
+// start of a pass; *bar_epoch counts the guided steps since then.
+int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, const double* noise, uint64_t seed, int t,
+                           double c1, double sqrt_alpha, double beta, const double* start_h, const double* goal_h,
+                           int rows, bool guided, unsigned* bar, unsigned* bar_epoch, cudaStream_t st) {
+  EDMP_REQUIRE(s->rows == rows, "guide tables were set for a different row count");
+  EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t out of range");
+  if (guided && ensure_work(s, rows, kHorizon - 2)) return 1;
+  if (s->tail_grid_cap == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    EDMP_CK(cudaGetDevice(&dev));
+    EDMP_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    EDMP_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tail_kernel, 64, 0));
+    EDMP_REQUIRE(per_sm > 0 && sms > 0, "step_tail_kernel does not fit an SM");
+    s->tail_grid_cap = per_sm * sms;
+  }
+  const int grid = std::min(rows, s->tail_grid_cap);
+  TailArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.x = x; a.xf = xf; a.eps = eps; a.noise = noise; a.seed = seed;
+  a.t = t; a.ensemble_rows = s->ensemble_rows; a.rows = rows; a.guided = guided ? 1 : 0;
+  a.c1 = c1; a.sqrt_alpha = sqrt_alpha; a.beta = beta;
+  for (int j = 0; j < 7; ++j) { a.start[j] = start_h[j]; a.goal[j] = goal_h[j]; }
+  a.ep = make_endpoints(start_h, goal_h);
+  a.sc = s->dev;
+  a.clearance = s->clearance; a.expansion = s->expansion; a.schedule = s->schedule;
+  a.method = s->method; a.grad_norm = s->grad_norm;
+  a.raw = s->raw; a.rowsq = s->rowsq;
+  a.bar = bar;
+  if (guided) { *bar_epoch += 1; a.bar_target = *bar_epoch * (unsigned)grid; }
+  launch_pdl(step_tail_kernel, dim3(grid), dim3(64), 0, st, a);
+  EDMP_CK(cudaGetLastError());
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -28,6 +29,7 @@ struct Scene {
   double* rowsq = nullptr;
   size_t rowsq_cap = 0;
   double* zero_tables = nullptr;
+  int tail_grid_cap = 0;    // CTAs of step_tail_kernel that are resident at once (its grid-wide barrier needs all of them)
 };
 
 int guide_init_constants();
@@ -41,6 +43,10 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
                           const double* start_h, const double* goal_h, int t, int rows,
                           double* grad_out, float* raw_out, double* x_state, float* xf_state,
                           cudaStream_t st);
+// posterior + (guided steps) gradient, norm mix, guided update, endpoints, float32 copy: one launch per reverse step
+int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, const double* noise, uint64_t seed, int t,
+                           double c1, double sqrt_alpha, double beta, const double* start_h, const double* goal_h,
+                           int rows, bool guided, unsigned* bar, unsigned* bar_epoch, cudaStream_t st);
 int guide_volumes_launch(Scene* s, const float* q, const double* start_h, const double* goal_h, int t,
                          int mode, int rows, int n, float* vol, cudaStream_t st);
 int guide_final_cost_launch(Scene* s, const double* traj, const double* start_h, const double* goal_h,

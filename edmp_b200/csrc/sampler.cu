@@ -5,11 +5,13 @@
 // float64 on the device like the reference's numpy state; the network sees a float32 copy
 // (diffusion.py:319).  Nothing returns to the host between steps.
 #include "common.cuh"
+#include "philox.cuh"
 #include "guide.h"
 #include "sampler.h"
 #include "unet.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace edmp {
@@ -22,33 +24,9 @@ struct Sampler {
   float* eps = nullptr;   // UNet output
   double* x_dev = nullptr;  // staging for the host-buffer entry point
   float* cost_dev = nullptr;
+  unsigned* bar = nullptr;  // grid-barrier counter of the fused per-step tail kernel (guide.cu)
   long long last_launches = 0;
 };
-
-// ---- Philox4x32-10 (counter based, one normal per element and step) ---------------------------
-__device__ __forceinline__ void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-  const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-  const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-}
-
-__device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t step, uint64_t idx) {
-  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), step, 0x45444D50u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  // Box-Muller on two 32-bit uniforms in (0, 1]
-  const float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;
-  const float u2 = ((float)c[1] + 1.0f) * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * logf(u1));
-  return (double)(r * cospif(2.0f * u2));
-}
 
 struct StepCoef {
   double c1;          // (1 - alpha) / sqrt(1 - alpha_bar)
@@ -112,7 +90,8 @@ int sampler_create(int T, double thresh, int max_rows, Sampler** out) {
   if (cudaMalloc(&s->xf, n * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&s->eps, n * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&s->x_dev, n * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&s->cost_dev, max_rows * sizeof(float)) != cudaSuccess) {
+      cudaMalloc(&s->cost_dev, max_rows * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&s->bar, sizeof(unsigned)) != cudaSuccess) {
     set_error("sampler_create: device allocation failed");
     sampler_destroy(s);
     return 1;
@@ -123,7 +102,7 @@ int sampler_create(int T, double thresh, int max_rows, Sampler** out) {
 
 void sampler_destroy(Sampler* s) {
   if (!s) return;
-  cudaFree(s->xf); cudaFree(s->eps); cudaFree(s->x_dev); cudaFree(s->cost_dev);
+  cudaFree(s->xf); cudaFree(s->eps); cudaFree(s->x_dev); cudaFree(s->cost_dev); cudaFree(s->bar);
   delete s;
 }
 
@@ -149,6 +128,12 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
   for (int j = 0; j < 7; ++j) { sc.start[j] = start[j]; sc.goal[j] = goal[j]; }
   sc.c1 = sc.sqrt_alpha = sc.beta = 0.0;
   long long launches = 0;
+  // one fused launch per step after the UNet (posterior, gradient, norm mix, guided update); EDMP_SPLIT_TAIL=1 keeps the
+  // three separate kernels (A/B, and the unguided path always uses posterior_kernel)
+  static const bool split_tail = getenv("EDMP_SPLIT_TAIL") != nullptr;
+  const bool fused = scene != nullptr && !split_tail;
+  unsigned bar_epoch = 0;
+  if (fused) EDMP_CK(cudaMemsetAsync(s->bar, 0, sizeof(unsigned), st));
   condition_kernel<<<blocks, threads, 0, st>>>(x, s->xf, sc, n);
   ++launches;
   for (int t = t_start; t > t_stop; --t) {
@@ -159,6 +144,14 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
     sc.sqrt_alpha = std::sqrt(a);
     sc.beta = s->beta[t - 1];
     const double* z = noise ? noise + (size_t)(t_start - t) * n : nullptr;
+    if (fused) {
+      // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)
+      if (guide_step_tail_launch(scene, x, s->xf, s->eps, z, seed, t, sc.c1, sc.sqrt_alpha, sc.beta, start, goal, rows,
+                                 (t % 2) == 0 && t >= 5, s->bar, &bar_epoch, st))
+        return 1;
+      ++launches;
+      continue;
+    }
     launch_pdl(posterior_kernel, dim3(blocks), dim3(threads), 0, st, x, s->xf, (const float*)s->eps, z, seed, t, ens, sc, n);
     ++launches;
     // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)

@@ -207,6 +207,7 @@ struct Layer {
   int tc_tiles = 0;             // column tiles (grid.y) of a tensor-core layer
   int cta_group = 1;            // LAYER_TC2: 2 = CTA pairs (cta_group::2)
   int b_pad = 0;                // LAYER_TC2 pairs: weight stages with shared resident zero slots
+  int nsplit = 1;               // LAYER_TC2: CTAs of a cluster that share one GroupNorm group (column split, small batches)
   size_t tc_smem = 0;
   Act pack_src, pack_dst;       // LAYER_PACK
   int temb_off = -1;  // offset into the per-t time-embedding row, -1 = none
@@ -237,6 +238,7 @@ struct UNet {
   bool cg2 = false;           // CTA pairs (cta_group::2) for the horizon 2 / 4 levels (large batches)
   bool pm2 = false;           // persistent position-major kernel (conv_pm2.cuh): one CTA per SM, all output channels per CTA
   bool chain = false;         // row-tile chaining between consecutive conv_tc2 launches (conv_tc2.cuh)
+  bool narrow = false;        // small batches: narrower column tiles / column-split GroupNorm groups (more tiles per layer)
   int* tile_done = nullptr;   // [layer][row tile] progress counters, zeroed at the start of every forward
   int tile_stride = 0;        // row tiles per layer in tile_done
   int sm_count = 148;
@@ -595,7 +597,10 @@ struct Builder {
       return ly.b_pad ? (size_t)nparts * ((size_t)n * (max_slots + 1) + 1) * slot_bytes : (size_t)n * max_slots * slot_bytes * nparts;
     };
     const size_t n_groups = t.cg == 8 ? t.ct / 8 : std::max(1, t.ct / t.cg);
-    const size_t part_bytes = ((size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) + n_groups) * 1024;   // GroupNorm pieces (mean, M2) per unit and row + group stats
+    v.nsplit = ly.nsplit;
+    ok = ok && (ly.nsplit == 1 || (cgrp == 1 && ly.nsplit * t.ct == t.cg && ly.nsplit <= 4 && t.mode != TC_BIAS));
+    // GroupNorm pieces (mean, M2) per unit and row + group stats (+ the statistics exchange buffer of a column split)
+    const size_t part_bytes = ((size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) + n_groups) * 1024 + (ly.nsplit > 1 ? 8192 : 0);
     const size_t budget = 232448 - 1024 - 7168 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
     v.b_stages = (b_bytes(3) + 3 * a_stage <= budget) ? 3 : ((b_bytes(2) + 2 * a_stage <= budget) ? 2 : 1);
     v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - b_bytes(v.b_stages)) / a_stage);
@@ -626,6 +631,14 @@ struct Builder {
     // L = 4 with one zero tap slot at either end; the accumulator is 256 columns per CTA
     const bool pair = u->cg2 && (L == 2 || L == 4) && cout >= 256;
     if (pair) ct = 256 / L;
+    // small batches: halve the column tiles while one wave of tiles still fits the machine (the K loop of a tile is
+    // the latency of the layer); below one GroupNorm group the CTAs of a cluster share the group (Tc2Args::nsplit)
+    int nsplit = 1;
+    if (u->tc2 && !pair && u->narrow) {
+      const int rts = (u->max_rows + kTcRows - 1) / kTcRows;
+      while (ct > 16 && (ct / 2) * 4 >= cg && rts * (cout / ct) * 2 <= u->sm_count) ct /= 2;
+      if (ct < cg) nsplit = cg / ct;
+    }
     Act y = new_act(u, out_name, cout, L, /*plain=*/false, /*tiled=*/true);
     ok = ok && y.ok;
     Layer ly;
@@ -648,6 +661,7 @@ struct Builder {
     ph.slots = j_end - j_begin + 1;
     ph.d_col = 0;
     ly.b_pad = padded ? 1 : 0;
+    ly.nsplit = nsplit;
     for (int li = 0; li < L; ++li) {
       const int lo_min = pair ? 0 : std::max(0, li - 2), lo_max = pair ? L - 1 : std::min(L - 1, li + 2);
       ph.sched[li].slot_begin = (int8_t)((lo_min - li + 2) - j_view);
@@ -708,6 +722,10 @@ struct Builder {
     const int lout = up ? ((2 * L == 8 || 2 * L == 14 || 2 * L == 26) ? 2 * L - 1 : 2 * L) : (L + 1) / 2;
     int ct = std::max(16, C / 8);
     if (u->tc2 && ct < 32 && lout * 32 <= 16 * kT2MaxUnits && !plain_out) ct = 32;
+    if (u->tc2 && u->narrow && !plain_out) {
+      const int rts = (u->max_rows + kTcRows - 1) / kTcRows;
+      while (ct > 16 && rts * (C / ct) * 2 <= u->sm_count) ct /= 2;
+    }
     Act y = new_act(u, name, C, lout, plain_out, !plain_out && !pm_out, pm_out);
     ok = ok && y.ok;
     Layer ly;
@@ -1089,6 +1107,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->pm2 = u->pm && getenv("EDMP_PM_V1") == nullptr;
   // pairs halve the number of schedulable tiles: only worth it when the batch still fills the machine
   u->cg2 = u->tc2 && getenv("EDMP_NO_CG2") == nullptr && (max_rows >= 4096 || getenv("EDMP_CG2") != nullptr);
+  u->narrow = u->tc2 && getenv("EDMP_NO_NARROW") == nullptr;
   {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
@@ -1262,6 +1281,13 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
       return;
     }
     const int n_tiles = a.n_row_tiles * a.n_col_tiles;
+    if (ly.nsplit > 1) {
+      // clusters of nsplit CTAs walk neighbouring column tiles (one GroupNorm group) of the same row tile in lockstep
+      dim3 gridc(std::min(n_tiles, u->sm_count / ly.nsplit * ly.nsplit));
+      if (u->tc_el == TC_EL_F16) launch_cluster(conv_tc2_kernel<TC_EL_F16, 1>, gridc, dim3(kT2Threads), ly.tc_smem, st, ly.nsplit, a);
+      else launch_cluster(conv_tc2_kernel<TC_EL_BF16, 1>, gridc, dim3(kT2Threads), ly.tc_smem, st, ly.nsplit, a);
+      return;
+    }
     dim3 grid(std::min(n_tiles, u->sm_count));
     if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
     else launch_pdl(conv_tc2_kernel<TC_EL_BF16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
@@ -1349,7 +1375,7 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
   Layer& ly = u->layers[op];
   const int ctas = ly.kind == LAYER_PM ? (u->pm2 ? std::min((rows + kPmRows - 1) / kPmRows, u->sm_count) : ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt))
                    : ly.kind == LAYER_TC2 ? (ly.cta_group == 2 ? 2 * std::min(((((rows + kTcRows - 1) / kTcRows) + 1) / 2) * ly.t2.n_col_tiles, u->sm_count / 2)
-                                                               : std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count))
+                                                               : std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count / ly.nsplit * ly.nsplit))
                                           : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;

@@ -1,0 +1,16 @@
+#!/bin/bash
+# round-2 development iteration: UNet parity tests (f16x3), per-CTA trace at 1020 rows, short bench at both batch sizes.
+# usage: bash tools/gpu_r2_iter.sh <tag> [pytest -k expression] [rows-per-guide list]
+TAG=${1:-it}; KEXPR=${2:-unet}; RPGS=${3:-"102 819"}; PREC=f16x3
+mkdir -p gpurun_out
+EDMP_TEST_PRECISIONS=$PREC timeout 900 python -m pytest tests -m gpu -x -q -k "$KEXPR" > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log
+tail -15 gpurun_out/${TAG}_tests.log
+timeout 300 python tools/tc_trace.py 1020 $PREC > gpurun_out/${TAG}_trace_1020.txt 2>&1
+for RPG in $RPGS; do
+  timeout 600 python bench.py --precision $PREC --rows-per-guide $RPG --no-cpu-baseline --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
+  python -c "
+import json,sys
+d=json.load(open('gpurun_out/${TAG}_bench_${RPG}.json'))
+print('rows/gpu', d['config']['rows_per_gpu'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'unet', d['unet'], 'roof', d['roofline']['kernel'], round(d['roofline']['frac'],4), d['clocks'])
+" || tail -5 gpurun_out/${TAG}_bench_${RPG}.err
+done
