@@ -41,6 +41,7 @@ SIGNATURES = {
                                         c_int, c_void_p, c_void_p]),
     "edmp_sampler_schedule": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "edmp_sampler_last_launches": (c_longlong, [c_void_p]),
+    "edmp_sampler_set_condition": (c_int, [c_void_p, c_int]),
     "edmp_sdf_scene_create": (c_int, [c_void_p, c_int, c_void_p, c_int, P(c_void_p)]),
     "edmp_sdf_scene_destroy": (None, [c_void_p]),
     "edmp_sdf_guide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -2,6 +2,7 @@
 #include "edmp_b200.h"
 
 #include <cstdlib>
+#include <mutex>
 #include <string>
 
 #include "common.cuh"
@@ -19,6 +20,22 @@ bool pdl_enabled() {
   // persistent kernels (profiles/r1_f16x3_pdl_ab.txt); EDMP_NO_PDL=1 falls back to plain stream order.
   static const bool on = std::getenv("EDMP_NO_PDL") == nullptr;
   return on;
+}
+static std::mutex g_once_mutex;
+bool once_per_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;   // unknown device: just redo the setup
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  const unsigned long long bit = 1ull << dev;
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+void once_per_device_failed(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return;
+  std::lock_guard<std::mutex> lock(g_once_mutex);
+  *mask &= ~(1ull << dev);
 }
 bool cluster_pdl_enabled() {
   static const bool on = std::getenv("EDMP_NO_PAIR_PDL") == nullptr;
@@ -159,6 +176,11 @@ int edmp_sampler_schedule(const edmp_sampler* s, double* beta_h, double* alpha_h
   return sampler_schedule(s->impl, beta_h, alpha_h, alpha_bar_h);
 }
 long long edmp_sampler_last_launches(const edmp_sampler* s) { return s ? sampler_last_launches(s->impl) : 0; }
+int edmp_sampler_set_condition(edmp_sampler* s, int condition) {
+  if (!s) { set_error("edmp_sampler_set_condition: null argument"); return 2; }
+  sampler_set_condition(s->impl, condition != 0);
+  return 0;
+}
 
 
 /* ---- sphere / signed-distance guide family (SURVEY.md section 8 a-S) ---------------------------------- */

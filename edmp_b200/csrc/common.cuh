@@ -40,6 +40,12 @@ constexpr int kMaxObs = 64;
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// One-time device setup (constant tables, kernel attributes) is PER DEVICE: a process that builds engines on cuda:0 and
+// then on cuda:1 must repeat it there.  once_per_device(mask) returns true the first time it is called with the current
+// device for this flag word (thread-safe; devices 0..63).
+bool once_per_device(unsigned long long* mask);
+void once_per_device_failed(unsigned long long* mask);   // the setup did not complete: try again next time
+
 bool pdl_enabled();
 bool cluster_pdl_enabled();   // EDMP_NO_PAIR_PDL=1 switches it off (A/B)
 

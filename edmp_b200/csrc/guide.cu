@@ -47,10 +47,17 @@ static const double kLinkDims[9][3] = {
 static const double kJointLoDeg[7] = {-166, -101, -166, -176, -166, -1, -166};
 static const double kJointHiDeg[7] = {166, 101, 166, -4, 166, 215, 166};
 
-static bool g_constants_ready = false;
+static unsigned long long g_constants_ready = 0;   // per-device flags (__constant__ symbols are per device)
 
+static int guide_upload_constants();
 int guide_init_constants() {
-  if (g_constants_ready) return 0;
+  if (!once_per_device(&g_constants_ready)) return 0;
+  const int rc = guide_upload_constants();
+  if (rc) once_per_device_failed(&g_constants_ready);
+  return rc;
+}
+
+static int guide_upload_constants() {
   float dh[7][4];
   for (int i = 0; i < 7; ++i) {
     float al = (float)kDhHost[i][2];
@@ -80,7 +87,6 @@ int guide_init_constants() {
   EDMP_CK(cudaMemcpyToSymbol(c_frame, fr, sizeof(fr)));
   EDMP_CK(cudaMemcpyToSymbol(c_joint_lo, lo, sizeof(lo)));
   EDMP_CK(cudaMemcpyToSymbol(c_joint_hi, hi, sizeof(hi)));
-  g_constants_ready = true;
   return 0;
 }
 
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(128) guide_apply_kernel(const float* __restric
 struct TailArgs {
   double* x; float* xf; const float* eps; const double* noise;
   unsigned long long seed;
-  int t, ensemble_rows, rows, guided;
+  int t, ensemble_rows, rows, guided, condition;
   double c1, sqrt_alpha, beta;
   double start[7], goal[7];
   EndPoints ep;
@@ -449,8 +455,8 @@ __global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ T
       double z = a.noise ? a.noise[i] : philox_normal(a.seed, (uint32_t)a.t, i);
       if (a.t == 1 && (row % a.ensemble_rows) == 0) z = 0.0;
       double v = (a.x[i] - a.c1 * (double)a.eps[i]) / a.sqrt_alpha + a.beta * z;
-      if (l == 0) v = a.start[j];
-      if (l == kHorizon - 1) v = a.goal[j];
+      if (a.condition && l == 0) v = a.start[j];
+      if (a.condition && l == kHorizon - 1) v = a.goal[j];
       s_x[e] = v;
       a.x[i] = v;
       a.xf[i] = (float)v;
@@ -754,7 +760,7 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
 // start of a pass; *bar_epoch counts the guided steps since then.
 int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, const double* noise, uint64_t seed, int t,
                            double c1, double sqrt_alpha, double beta, const double* start_h, const double* goal_h,
-                           int rows, bool guided, unsigned* bar, unsigned* bar_epoch, cudaStream_t st) {
+                           int rows, bool guided, bool condition, unsigned* bar, unsigned* bar_epoch, cudaStream_t st) {
   EDMP_REQUIRE(s->rows == rows, "guide tables were set for a different row count");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t out of range");
   if (guided && ensure_work(s, rows, kHorizon - 2)) return 1;
@@ -770,7 +776,7 @@ int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, con
   TailArgs a;
   std::memset(&a, 0, sizeof(a));
   a.x = x; a.xf = xf; a.eps = eps; a.noise = noise; a.seed = seed;
-  a.t = t; a.ensemble_rows = s->ensemble_rows; a.rows = rows; a.guided = guided ? 1 : 0;
+  a.t = t; a.ensemble_rows = s->ensemble_rows; a.rows = rows; a.guided = guided ? 1 : 0; a.condition = condition ? 1 : 0;
   a.c1 = c1; a.sqrt_alpha = sqrt_alpha; a.beta = beta;
   for (int j = 0; j < 7; ++j) { a.start[j] = start_h[j]; a.goal[j] = goal_h[j]; }
   a.ep = make_endpoints(start_h, goal_h);

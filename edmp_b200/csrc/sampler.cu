@@ -26,6 +26,7 @@ struct Sampler {
   float* cost_dev = nullptr;
   unsigned* bar = nullptr;  // grid-barrier counter of the fused per-step tail kernel (guide.cu)
   long long last_launches = 0;
+  bool condition = true;    // overwrite the first / last waypoint with start / goal every step (diffusion.py:306-307,:347-349)
 };
 
 struct StepCoef {
@@ -36,14 +37,14 @@ struct StepCoef {
 };
 
 // X[:, :, 0] = start, X[:, :, -1] = goal (diffusion.py:306-307), and the float32 copy
-__global__ void condition_kernel(double* __restrict__ x, float* __restrict__ xf, StepCoef sc, size_t n) {
+__global__ void condition_kernel(double* __restrict__ x, float* __restrict__ xf, StepCoef sc, bool condition, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int e = (int)(i % kRowElems);
   const int j = e / kHorizon, l = e % kHorizon;
   double v = x[i];
-  if (l == 0) v = sc.start[j];
-  if (l == kHorizon - 1) v = sc.goal[j];
+  if (condition && l == 0) v = sc.start[j];
+  if (condition && l == kHorizon - 1) v = sc.goal[j];
   x[i] = v;
   xf[i] = (float)v;
 }
@@ -53,7 +54,7 @@ __global__ void condition_kernel(double* __restrict__ x, float* __restrict__ xf,
 // numpy-1.x semantics); endpoints re-conditioned (:347-349).
 __global__ void posterior_kernel(double* __restrict__ x, float* __restrict__ xf,
                                  const float* __restrict__ eps, const double* __restrict__ noise,
-                                 uint64_t seed, int t, int ensemble_rows, StepCoef sc, size_t n) {
+                                 uint64_t seed, int t, int ensemble_rows, StepCoef sc, bool condition, size_t n) {
   pdl_launch_dependents();
   pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,8 +65,8 @@ __global__ void posterior_kernel(double* __restrict__ x, float* __restrict__ xf,
   double z = noise ? noise[i] : philox_normal(seed, (uint32_t)t, i);
   if (t == 1 && (row % ensemble_rows) == 0) z = 0.0;
   double v = (x[i] - sc.c1 * (double)eps[i]) / sc.sqrt_alpha + sc.beta * z;
-  if (l == 0) v = sc.start[j];
-  if (l == kHorizon - 1) v = sc.goal[j];
+  if (condition && l == 0) v = sc.start[j];
+  if (condition && l == kHorizon - 1) v = sc.goal[j];
   x[i] = v;
   xf[i] = (float)v;
 }
@@ -112,13 +113,14 @@ int sampler_schedule(const Sampler* s, double* b, double* a, double* ab) {
 }
 
 long long sampler_last_launches(const Sampler* s) { return s->last_launches; }
+void sampler_set_condition(Sampler* s, bool condition) { s->condition = condition; }
 
 int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* start, const double* goal,
                   const double* noise, uint64_t seed, int rows, int t_start, int t_stop, float* final_cost,
                   cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && rows <= s->max_rows, "rows exceeds the sampler's max_rows");
   EDMP_REQUIRE(t_start <= s->T && t_stop >= 0 && t_start > t_stop, "bad step range");
-  EDMP_REQUIRE(start && goal, "start/goal are required (condition=True path)");
+  EDMP_REQUIRE(start && goal, "start/goal are required (the guide's swept volumes use them also when condition=False)");
   if (scene) EDMP_REQUIRE(scene->rows == rows, "guide tables were set for a different row count");
   const int ens = scene ? scene->ensemble_rows : rows;
   const size_t n = (size_t)rows * kRowElems;
@@ -134,7 +136,7 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
   const bool fused = scene != nullptr && !split_tail;
   unsigned bar_epoch = 0;
   if (fused) EDMP_CK(cudaMemsetAsync(s->bar, 0, sizeof(unsigned), st));
-  condition_kernel<<<blocks, threads, 0, st>>>(x, s->xf, sc, n);
+  condition_kernel<<<blocks, threads, 0, st>>>(x, s->xf, sc, s->condition, n);
   ++launches;
   for (int t = t_start; t > t_stop; --t) {
     if (unet_forward(u, s->xf, t, rows, s->eps, st)) return 1;
@@ -147,12 +149,12 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
     if (fused) {
       // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)
       if (guide_step_tail_launch(scene, x, s->xf, s->eps, z, seed, t, sc.c1, sc.sqrt_alpha, sc.beta, start, goal, rows,
-                                 (t % 2) == 0 && t >= 5, s->bar, &bar_epoch, st))
+                                 (t % 2) == 0 && t >= 5, s->condition, s->bar, &bar_epoch, st))
         return 1;
       ++launches;
       continue;
     }
-    launch_pdl(posterior_kernel, dim3(blocks), dim3(threads), 0, st, x, s->xf, (const float*)s->eps, z, seed, t, ens, sc, n);
+    launch_pdl(posterior_kernel, dim3(blocks), dim3(threads), 0, st, x, s->xf, (const float*)s->eps, z, seed, t, ens, sc, s->condition, n);
     ++launches;
     // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)
     if (scene && (t % 2) == 0 && t >= 5) {

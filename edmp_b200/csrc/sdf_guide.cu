@@ -352,14 +352,22 @@ static void quat_xyzw_to_rinv(const double* qv, float* rinv) {
   for (int i = 0; i < 9; ++i) rinv[i] = (float)R[i];
 }
 
+// the sphere table is a __constant__ symbol: per device
+static unsigned long long g_sdf_tables_ready = 0;
+static int sdf_upload_tables() {
+  if (!once_per_device(&g_sdf_tables_ready)) return 0;
+  if (cudaMemcpyToSymbol(c_spheres, kSphereTable, sizeof(kSphereTable)) != cudaSuccess) {
+    once_per_device_failed(&g_sdf_tables_ready);
+    set_error("sdf: uploading the collision-sphere table failed");
+    return 1;
+  }
+  return 0;
+}
+
 int sdf_scene_create(const double* boxes_h, int n_boxes, const double* cyls_h, int n_cyls, SdfScene** out) {
   EDMP_REQUIRE(n_boxes >= 0 && n_cyls >= 0 && n_boxes + n_cyls <= kSdfMaxPrims, "at most 64 primitives");
   EDMP_REQUIRE((n_boxes == 0 || boxes_h) && (n_cyls == 0 || cyls_h), "null primitive array");
-  static bool table_up = false;
-  if (!table_up) {
-    EDMP_CK(cudaMemcpyToSymbol(c_spheres, kSphereTable, sizeof(kSphereTable)));
-    table_up = true;
-  }
+  if (sdf_upload_tables()) return 1;
   std::vector<SdfPrim> prims((size_t)n_boxes + n_cyls);
   for (int i = 0; i < n_boxes; ++i) {          // [xyz, quaternion xyzw, dims]  (the reference's obstacle_config rows)
     const double* b = boxes_h + (size_t)i * 10;
@@ -405,11 +413,7 @@ int sdf_guide_launch(SdfScene* s, const float* q_d, int n, int rows, float margi
 int sdf_cloud_launch(const float* q_d, int n, int rows, const float* points_d, int n_points, float* clearance_d,
                      cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && n > 0 && n <= 50 && n_points > 0, "1..50 waypoints per row and a non-empty cloud");
-  static bool table_up = false;
-  if (!table_up) {
-    EDMP_CK(cudaMemcpyToSymbol(c_spheres, kSphereTable, sizeof(kSphereTable)));
-    table_up = true;
-  }
+  if (sdf_upload_tables()) return 1;
   sdf_cloud_kernel<<<rows, kSdfThreads, 0, st>>>(q_d, n, rows, reinterpret_cast<const float4*>(points_d), n_points, clearance_d);
   EDMP_CK(cudaGetLastError());
   return 0;

@@ -1071,8 +1071,8 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->tc_el = (precision == EDMP_PRECISION_BF16X3 || precision == EDMP_PRECISION_BF16) ? TC_EL_BF16
              : (precision == EDMP_PRECISION_F16X3 || precision == EDMP_PRECISION_F16) ? TC_EL_F16 : TC_EL_TF32;
   if (u->tc) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;   // cudaFuncSetAttribute is per device
+    if (once_per_device(&attr_set)) {
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
@@ -1088,7 +1088,6 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
-      attr_set = true;
     }
   }
   Builder b{u, params, &pw};

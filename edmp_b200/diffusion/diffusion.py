@@ -63,7 +63,7 @@ class Diffusion:
         return np.random.multivariate_normal(mean=np.zeros(traj_len), cov=np.eye(traj_len), size=size)
 
     def run_steps(self, model, guide, x, start, goal, t_start, t_stop, noise=None, seed=0,
-                  guidance_schedule=None, ensemble_rows=None, want_cost=False):
+                  guidance_schedule=None, ensemble_rows=None, want_cost=False, condition=True):
         """Device loop over steps t_start .. t_stop+1 on x ([B,7,50] float64 CUDA tensor, in place).
         ``noise``: float64 CUDA tensor [t_start-t_stop, B, 7, 50] or None (Philox with ``seed``)."""
         dev = _lib.require_cuda(self.device)
@@ -79,6 +79,7 @@ class Diffusion:
             s_arr, s_ptr = _lib.host_f64(start)
             g_arr, g_ptr = _lib.host_f64(goal)
             cost = torch.empty(B, device=dev, dtype=torch.float32) if (want_cost and guide is not None) else None
+            _lib.check(lib.edmp_sampler_set_condition(sampler, 1 if condition else 0), "edmp_sampler_set_condition")
             _lib.check(lib.edmp_sample_guided(
                 sampler, unet, scene, ctypes.c_void_p(x.data_ptr()), s_ptr, g_ptr,
                 ctypes.c_void_p(noise.data_ptr()) if noise is not None else None,
@@ -95,8 +96,6 @@ class Diffusion:
         "numpy" | "philox" | (x_T, [z_255 .. z_1]) to replay recorded draws."""
         if traj_len != 50 or num_channels != 7:
             raise ValueError("the engine is compiled for 50 waypoints x 7 joints (cfg1.yaml:16-17)")
-        if not condition:
-            raise NotImplementedError("condition=False is not used by infer_serial.py")
         dev = _lib.require_cuda(self.device)
         B = int(batch_size)
         mode = noise if noise is not None else self.noise_mode
@@ -118,7 +117,7 @@ class Diffusion:
         x = torch.as_tensor(x_T, dtype=torch.float64).to(dev).contiguous()
         z = torch.as_tensor(tape).to(dev).contiguous() if tape is not None else None
         cost = self.run_steps(model, guide, x, np.asarray(start)[:], np.asarray(goal)[:], self.T, 0, noise=z,
-                              seed=seed, guidance_schedule=guidance_schedule, want_cost=True)
+                              seed=seed, guidance_schedule=guidance_schedule, want_cost=True, condition=condition)
         self.last_final_cost = cost
         out = x.cpu().numpy()
         return out.copy()
@@ -131,5 +130,9 @@ class Diffusion:
         x = torch.as_tensor(x_T, dtype=torch.float64).to(dev).contiguous()
         z = torch.as_tensor(tape).to(dev).contiguous()
         model.train(False)
-        self.run_steps(model, None, x, start, goal, self.T, 0, noise=z)
+        if start is None or goal is None:
+            if condition:
+                raise ValueError("condition=True needs start and goal")
+            start, goal = np.zeros(num_channels), np.zeros(num_channels)   # unused without conditioning and a guide
+        self.run_steps(model, None, x, start, goal, self.T, 0, noise=z, condition=condition)
         return x.cpu().numpy()[0]

@@ -81,9 +81,16 @@ def _default_init(table, generator=None):
 class TemporalUNet:
 
     def __init__(self, model_name, input_dim, time_dim, device, dims=(32, 64, 128, 256),
-                 precision="fp32", max_rows=64):
+                 precision=None, max_rows=64):
+        """``precision``: arithmetic mode of the contractions.  The reference's call site passes none
+        (infer_serial.py:50), so the default is the benchmarked parity-grade tensor-core mode: ``f16x3`` (tcgen05,
+        IEEE-half hi/lo operand split), or whatever ``EDMP_PRECISION`` names (``fp32`` = CUDA-core kernels)."""
         if time_dim != TIME_DIM:
             raise ValueError("time_dim must be 32 (infer_serial.py:50)")
+        if precision is None:
+            precision = os.environ.get("EDMP_PRECISION", "f16x3")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("unknown precision %r (one of %s)" % (precision, sorted(_lib.PRECISIONS)))
         self.input_dim, self.time_dim, self.dims = int(input_dim), int(time_dim), tuple(int(d) for d in dims)
         self.device = device
         self.precision = precision

@@ -8,6 +8,7 @@ the closed form of the reference's autograd result, evaluated in libedmp_b200.so
 import ctypes
 import os
 import re
+import warnings
 
 import numpy as np
 import torch
@@ -36,15 +37,31 @@ def link_dimensions_from_meshes(folder):
     return np.array(dims)
 
 
+#: where the link-box extents of the last guide came from: "pybullet_data" (what the reference measures,
+#: lib/guide.py:245) or "builtin" (the library's table: robofin's hd collision meshes, SURVEY.md 8c -- the same
+#: geometry at another tessellation, extents differ by up to a few mm from pybullet_data's)
+LINK_DIMENSIONS_SOURCE = None
+_warned_builtin = False
+
+
 def _default_link_dimensions():
+    global LINK_DIMENSIONS_SOURCE, _warned_builtin
     try:
         import pybullet_data
+    except ImportError:
+        pybullet_data = None
+    if pybullet_data is not None:
         folder = os.path.join(pybullet_data.getDataPath(), "franka_panda", "meshes", "collision")
         if os.path.isdir(folder):
-            return link_dimensions_from_meshes(folder)
-    except Exception:
-        pass
-    return None  # the library's built-in table (robofin hd collision meshes)
+            LINK_DIMENSIONS_SOURCE = "pybullet_data"
+            return link_dimensions_from_meshes(folder)   # a broken mesh folder raises: do not hide it
+    LINK_DIMENSIONS_SOURCE = "builtin"
+    if not _warned_builtin:
+        _warned_builtin = True
+        warnings.warn("edmp_b200: pybullet_data is not installed; link-box extents come from the built-in table "
+                      "(robofin hd collision meshes), which differs from a stock reference install by up to a few mm. "
+                      "Pass link_dimensions= to IntersectionVolumeGuide to pin them.", RuntimeWarning, stacklevel=3)
+    return None
 
 
 class IntersectionVolumeGuide:
@@ -105,11 +122,17 @@ class IntersectionVolumeGuide:
         if ensemble_rows is None:
             ensemble_rows = self.ensemble_rows
         ens = int(ensemble_rows if ensemble_rows is not None else rows)
-        key = (rows, ens, id(sched))
+        g = self.guide_cfgs
+        arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in
+                (g["clearance"], g["expansion"], sched, g["guidance_method"], g["grad_norm"])]
+        # keyed on the identity AND a content fingerprint of all five tables (the arrays are kept referenced, so an id()
+        # cannot be recycled by a temporary; the two sums catch in-place edits of guide_cfgs between calls at ~1 ms per
+        # 2M-entry table -- a cryptographic hash of the 50 MB of an 8190-row ensemble would cost 50 ms per call)
+        srcs = (g["clearance"], g["expansion"], sched, g["guidance_method"], g["grad_norm"])
+        finger = tuple((float(a.sum()), float(a.reshape(-1)[::13].sum())) for a in arrs)
+        key = (rows, ens, tuple(id(o) for o in srcs), finger)
+        self._tables_refs = srcs
         if self._tables_key != key:
-            g = self.guide_cfgs
-            arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in
-                    (g["clearance"], g["expansion"], sched, g["guidance_method"], g["grad_norm"])]
             for a, width in zip(arrs, (255, 255, 255, None, None)):
                 if a.shape[0] != rows or (width and a.shape[1] != width):
                     raise ValueError("guide table shape %s does not match rows=%d" % (a.shape, rows))

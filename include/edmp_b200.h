@@ -146,6 +146,10 @@ int edmp_sample_guided_host(edmp_sampler* s, edmp_unet* u, edmp_scene* scene, do
 int edmp_sampler_schedule(const edmp_sampler* s, double* beta_h, double* alpha_h, double* alpha_bar_h);
 /* kernels launched by the last edmp_sample_guided[_host] call */
 long long edmp_sampler_last_launches(const edmp_sampler* s);
+/* condition != 0 (the default): the first / last waypoint of every row is overwritten with start / goal before the
+ * first step and after every step (diffusion.py:306-307,:347-349 `if condition:`); 0: the endpoints diffuse freely
+ * (start / goal are then only the padding waypoints of the guide's swept volumes, lib/guide.py:484-492). */
+int edmp_sampler_set_condition(edmp_sampler* s, int condition);
 
 /* ---- sphere / signed-distance guide family (SURVEY.md section 8 a-S; BASELINE.json configs[4]) ---------------
  * Not on the reference's infer_serial.py path (its guide is the AABB-volume one above); specified by code the

@@ -36,12 +36,22 @@ DIMS = (32, 64, 128, 256, 512, 512)        # reference infer_serial.py:50
 GOAL_TRUST_REGION = front_end.GOAL_TRUST_REGION   # reference infer_serial.py:125 (hard-coded there too)
 
 
+SYNTHETIC_SCENES_PER_TYPE = 2   # size of the synthetic problem set per scene type (what "all scenes" means for it)
+
+
+class _EveryType(dict):
+    def __missing__(self, key):
+        return SYNTHETIC_SCENES_PER_TYPE
+
+
 class SyntheticProblems:
     """Stand-in for datasets.load_test_dataset.TestDataset: fetch_data(scene_num, scene_type) returns the fields the
-    entry point uses (obstacle_config [no,10], start [7], all_ik_goals [k,7])."""
+    entry point uses (obstacle_config [no,10], start [7], all_ik_goals [k,7]); data_nums[scene_type] = problems per type
+    like the reference loader's attribute (infer_serial.py:98)."""
 
     def __init__(self, seed=0):
         self.seed = int(seed)
+        self.data_nums = _EveryType()
 
     def fetch_data(self, scene_num, scene_type="tabletop"):
         if scene_type == "tabletop":
@@ -64,11 +74,24 @@ def load_problems(cfg):
     real = TestDataset(ds["dataset_type"], d_path=ds["path"])
 
     class _Adapter:
+        data_nums = real.data_nums
+
         def fetch_data(self, scene_num, scene_type):
             obstacle_config, _, _, _, _, start, goals = real.fetch_data(scene_num=scene_num, scene_type=scene_type)
             return obstacle_config, start, goals
 
     return _Adapter(), ds["scene_types"]
+
+
+def scenes_per_type(cfg, problems, scene_type):
+    """How many problems of `scene_type` to run.  The reference always walks the whole set (infer_serial.py:98 loops
+    over dataset.data_nums[scene_type]; its cfg1.yaml says `num_scenes_per_type: -1  # -1 implies all scenes`), so a
+    missing key or a value <= 0 means ALL; a positive value caps the walk."""
+    total = int(problems.data_nums[scene_type])
+    want = cfg["dataset"].get("num_scenes_per_type", -1)
+    if want is None or int(want) <= 0:
+        return total
+    return min(int(want), total)
 
 
 def load_model(cfg, device, precision):
@@ -120,12 +143,11 @@ def main(argv=None):
     diffuser = Diffusion(T=cfg["model"]["T"], device=device)
     diffuser.noise_mode = args.noise
     model = load_model(cfg, device, args.precision)
-    n_scenes = cfg["dataset"].get("num_scenes_per_type", 1)
     save_dir = cfg["general"].get("save_dir")
 
     results, n_success = [], 0
     for scene_type in scene_types:
-        for scene_num in range(n_scenes):
+        for scene_num in range(scenes_per_type(cfg, problems, scene_type)):
             t_plan = time.time()
             obstacle_config, start, ik_goals = problems.fetch_data(scene_num, scene_type)
             guide = IntersectionVolumeGuide(obstacle_config=obstacle_config, device=device, guide_cfgs=guide_cfgs,

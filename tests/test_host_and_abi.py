@@ -131,6 +131,32 @@ def test_infer_serial_cfg_surface():
         infer_serial.load_problems(shipped)   # 'hybrid' needs the reference's loader + downloads
 
 
+def test_infer_serial_walks_every_scene_by_default():
+    """`num_scenes_per_type: -1` (the shipped cfg1.yaml) and a missing key mean ALL scenes, like the reference's loop
+    over dataset.data_nums[scene_type] (infer_serial.py:98); a positive value caps the walk."""
+    import infer_serial
+    from edmp_b200 import YamlConfig
+
+    class Problems:
+        data_nums = {"tabletop": 7, "cubby": 3}
+
+    shipped = YamlConfig(os.path.join(ROOT, "benchmark", "cfgs", "cfg1.yaml"))
+    assert shipped["dataset"]["num_scenes_per_type"] == -1
+    assert infer_serial.scenes_per_type(shipped, Problems, "tabletop") == 7
+    assert infer_serial.scenes_per_type(shipped, Problems, "cubby") == 3
+    cfg = {"dataset": {}}
+    assert infer_serial.scenes_per_type(cfg, Problems, "tabletop") == 7
+    cfg = {"dataset": {"num_scenes_per_type": 2}}
+    assert infer_serial.scenes_per_type(cfg, Problems, "tabletop") == 2
+    assert infer_serial.scenes_per_type(cfg, Problems, "cubby") == 2
+    cfg = {"dataset": {"num_scenes_per_type": 100}}
+    assert infer_serial.scenes_per_type(cfg, Problems, "cubby") == 3
+    # the synthetic problem source has a documented size for every scene type
+    syn = infer_serial.SyntheticProblems()
+    assert infer_serial.scenes_per_type({"dataset": {"num_scenes_per_type": -1}}, syn, "tabletop") == \
+        infer_serial.SYNTHETIC_SCENES_PER_TYPE > 0
+
+
 def test_obstacle_flattening_like_the_reference_loader():
     """edmp_b200.scene.flatten_obstacles against a literal restatement of datasets/load_test_dataset.py:105-151 on the
     fields the reference reads off geometrout's Cuboid / Cylinder (center, wxyz quaternion, dims | radius, height)."""
