@@ -26,6 +26,7 @@ SIGNATURES = {
     "edmp_unet_op_kernel": (c_char_p, [c_void_p, c_int]),
     "edmp_unet_tc_trace": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, P(c_int), c_void_p]),
     "edmp_unet_precision": (c_int, [c_void_p]),
+    "edmp_unet_range_status": (c_int, [c_void_p, P(c_int), c_void_p]),
     "edmp_unet_launches_per_forward": (c_int, [c_void_p]),
     "edmp_scene_create": (c_int, [c_void_p, c_int, c_void_p, P(c_void_p)]),
     "edmp_scene_destroy": (None, [c_void_p]),

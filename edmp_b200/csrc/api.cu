@@ -103,6 +103,10 @@ int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max
 const char* edmp_unet_op_name(const edmp_unet* u, int i) { return u ? unet_op_name(u->impl, i) : nullptr; }
 const char* edmp_unet_op_kernel(const edmp_unet* u, int i) { return u ? unet_op_kernel(u->impl, i) : nullptr; }
 int edmp_unet_precision(const edmp_unet* u) { return u ? unet_precision(u->impl) : -1; }
+int edmp_unet_range_status(edmp_unet* u, int* overflow, void* stream) {
+  if (!u || !overflow) { set_error("edmp_unet_range_status: null argument"); return 2; }
+  EDMP_TRY(unet_range_status(u->impl, overflow, static_cast<cudaStream_t>(stream)));
+}
 int edmp_unet_launches_per_forward(const edmp_unet* u) { return u ? unet_launches(u->impl) : 0; }
 
 int edmp_scene_create(const double* obstacle_cfg_h, int n_obs, const double* link_dims_h, edmp_scene** out) {

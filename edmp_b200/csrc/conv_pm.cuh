@@ -82,6 +82,7 @@ struct PmArgs {
   float* eps;                       // [rows][7][lout]
   int rows;
   long long* dbg;                   // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
+  unsigned* range_flag;             // set when a stored IEEE-half hi part is infinite (conv_tc.cuh range_track), may be null
 };
 
 __device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, int rby) {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kPmThreads, 2) conv_pm_kernel(const __grid_con
 // One thread per (row, position).
 template <int EL>
 __global__ void pm_pack_input_kernel(const float* __restrict__ x, int rows, int L, void* __restrict__ hi,
-                                     void* __restrict__ lo) {
+                                     void* __restrict__ lo, unsigned* __restrict__ range_flag) {
   pdl_launch_dependents();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,6 +419,11 @@ __global__ void pm_pack_input_kernel(const float* __restrict__ x, int rows, int 
   for (int e = 0; e < 16; ++e) v[e] = e < kDof ? x[((size_t)row * kDof + e) * L + l] : 0.0f;
   uint4 h[4], r[4];
   tc_split_store<EL>(v, lo != nullptr, h, r);
+  {
+    uint32_t hmax = 0;   // the network input itself must fit the operand range (|x| <= 65504 in the half modes)
+    range_track<EL>(hmax, h[0].x); range_track<EL>(hmax, h[0].y); range_track<EL>(hmax, h[0].z); range_track<EL>(hmax, h[0].w);
+    range_report<EL>(hmax, range_flag);
+  }
   const int rb = row / kPmRows, rr = row % kPmRows;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {

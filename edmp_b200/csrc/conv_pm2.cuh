@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     (void)acc_cols;
     uint32_t k = (uint32_t)grp;
     long long w_full = 0, t_busy = 0, t_stats = 0;
+    uint32_t hmax = 0;   // largest |hi| half pattern stored (operand range check, conv_tc.cuh)
     for (int rb = blockIdx.x + grp * gridDim.x; rb < n_blocks; rb += kPm2Groups * gridDim.x, k += kPm2Groups) {
       const uint32_t use = k >> 1;
       const int grow = rb * kPmRows + row;        // global trajectory row
@@ -319,6 +320,10 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
             if (o_hi || (!is_aux && a.tc_hi)) {
               uint4 h[4], l[4];
               tc_split_store2<EL>(v2, (is_aux ? a.aux_lo : (a.tc_hi ? a.tc_lo : a.out_lo)) != nullptr, h, l);
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                range_track<EL>(hmax, h[m].x); range_track<EL>(hmax, h[m].y); range_track<EL>(hmax, h[m].z); range_track<EL>(hmax, h[m].w);
+              }
               if (o_hi) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       if (lane == 0) umma::mbar_arrive(bar_acc_empty + grp);
       if (dbg) t_busy += clock64() - t_start;
     }
+    range_report<EL>(hmax, a.range_flag);
     if (dbg && et == 0 && grp == 0) { dbg[6] = w_full; dbg[8] = t_busy; dbg[9] = t_stats; dbg[10] = 0; dbg[11] = t_busy - t_stats; dbg[12] = 0; }
     umma::tc_fence_before();
   }

@@ -158,6 +158,17 @@ template <int EL> __device__ __forceinline__ float2 unpack16x2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
+// IEEE-half operand range (f16x3 / f16 modes): activations are split hi + lo UN-scaled, so a value beyond
+// +-65504 becomes an infinite hi part and the forward silently turns to NaN.  The epilogues keep the largest |hi| bit
+// pattern they store (two halves per word: one LOP3 + one VIMNMX per pair) and raise a device flag at the end of the
+// kernel if it reached the infinity / NaN patterns; edmp_unet_range_status reads it.  BF16 / TF32 have fp32's range.
+template <int EL> __device__ __forceinline__ void range_track(uint32_t& hmax, uint32_t packed_hi) {
+  if (EL == TC_EL_F16) hmax = __vmaxu2(hmax, packed_hi & 0x7FFF7FFFu);
+}
+template <int EL> __device__ __forceinline__ void range_report(uint32_t hmax, unsigned* flag) {
+  if (EL == TC_EL_F16 && flag != nullptr && ((hmax & 0xFFFFu) >= 0x7C00u || (hmax >> 16) >= 0x7C00u)) atomicOr(flag, 1u);
+}
+
 // split 16 fp32 values into hi/lo parts in the operand element type; writes kUnitChunks 16-byte chunks each
 template <int EL>
 __device__ __forceinline__ void tc_split_store(const float (&v)[16], bool want_lo, uint4* hi, uint4* lo) {

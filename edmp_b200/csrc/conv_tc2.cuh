@@ -85,6 +85,7 @@ struct Tc2Args {
   void *out_hi, *out_lo;          // tiled output (or position-major images when out_pm)
   int out_pm;
   long long* dbg;                 // optional [ctas][16] clock64 stamps / counters, normally null
+  unsigned* range_flag;           // set when a stored IEEE-half hi part is infinite (conv_tc.cuh range_track), may be null
 };
 
 namespace t2 {
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (gw >> 4)));
     float* s_xg = my_part + (n_pieces_alloc + n_groups) * 256;   // nsplit > 1: [tile parity][source rank][mean | M2][128 rows]
     uint32_t xg_par = 0, xg_ph = 0;
+    uint32_t hmax = 0;                                    // largest |hi| half pattern stored (operand range check)
     uint32_t buf = 0, fph = 0;
     long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
     int tile_par = 0;
@@ -787,6 +789,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 float x0, x1, d0, d1;
                 f2::upk(v2[e], x0, x1);
                 hh[e] = pack16x2<EL>(x0, x1);
+                range_track<EL>(hmax, hh[e]);
                 const float2 hf = unpack16x2<EL>(hh[e]);
                 f2::upk(f2::sub(v2[e], f2::pk(hf.x, hf.y)), d0, d1);
                 ll[e] = pack16x2<EL>(d0, d1);
@@ -824,6 +827,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) fph ^= 1; } else { fph ^= 1; }
     }
     if (dbg && et == 0) { dbg[6] = w_full; dbg[8] = t_busy; dbg[9] = t_stats; dbg[10] = t_bar; dbg[11] = t_fin; dbg[12] = t_par; }
+    range_report<EL>(hmax, a.range_flag);
     umma::tc_fence_before();
   }
   __syncthreads();

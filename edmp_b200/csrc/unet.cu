@@ -244,6 +244,7 @@ struct UNet {
   int sm_count = 148;
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
+  unsigned* range_flag = nullptr;   // device flag: an activation left the IEEE-half operand range (f16x3 / f16 modes)
   int max_rows = 0;
   int n_launches = 0;
   std::vector<void*> dev_allocs;
@@ -1174,6 +1175,10 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
     u->final_b = b.vec("final_conv.1.bias", kDof);
   }
 
+  if (u->tc_el == TC_EL_F16) {
+    b.ok = b.ok && cudaMalloc(&u->range_flag, sizeof(unsigned)) == cudaSuccess;
+    if (b.ok) { u->dev_allocs.push_back(u->range_flag); cudaMemset(u->range_flag, 0, sizeof(unsigned)); }
+  }
   // progress counters of the chained conv_tc2 launches
   u->chain = u->tc2 && pdl_enabled() && getenv("EDMP_NO_CHAIN") == nullptr;
   u->tile_stride = ((max_rows + kTcRows - 1) / kTcRows + 1) & ~1;
@@ -1233,6 +1238,19 @@ void unet_destroy(UNet* u) {
 }
 
 int unet_precision(const UNet* u) { return u->precision; }
+
+// Reads and clears the operand-range flag (synchronises the stream): 1 = some activation of a forward since the last
+// call exceeded the IEEE-half range and the results are not to be trusted (use tf32x3 / bf16x3 / fp32 for this model).
+int unet_range_status(UNet* u, int* overflow, cudaStream_t st) {
+  *overflow = 0;
+  if (!u->range_flag) return 0;
+  unsigned v = 0;
+  EDMP_CK(cudaMemcpyAsync(&v, u->range_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  EDMP_CK(cudaStreamSynchronize(st));
+  if (v) EDMP_CK(cudaMemsetAsync(u->range_flag, 0, sizeof(unsigned), st));
+  *overflow = v ? 1 : 0;
+  return 0;
+}
 int unet_launches(const UNet* u) { return u->n_launches; }
 
 static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row, int rows, float* eps, cudaStream_t st) {
@@ -1243,6 +1261,7 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     if (ly.pm_final) a.eps = eps;
     a.dbg = u->dbg;
+    a.range_flag = u->range_flag;
     if (u->pm2) {
       dim3 grid2(std::min((rows + kPmRows - 1) / kPmRows, u->sm_count));
       auto k2 = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm2_kernel<TC_EL_F16, 4> : conv_pm2_kernel<TC_EL_F16, 8>)
@@ -1257,7 +1276,7 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
   } else if (ly.kind == LAYER_PM_PACK) {
     const int total = rows * ly.pack_src.L;
     auto k = u->tc_el == TC_EL_F16 ? pm_pack_input_kernel<TC_EL_F16> : pm_pack_input_kernel<TC_EL_BF16>;
-    launch_pdl(k, dim3((total + 255) / 256), dim3(256), 0, st, x, rows, ly.pack_src.L, ly.pack_dst.phi, ly.pack_dst.plo);
+    launch_pdl(k, dim3((total + 255) / 256), dim3(256), 0, st, x, rows, ly.pack_src.L, ly.pack_dst.phi, ly.pack_dst.plo, u->range_flag);
   } else if (ly.kind == LAYER_SIMT) {
     ConvArgs a = ly.args;
     a.rows = rows;
@@ -1270,6 +1289,7 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.rows = rows;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     a.dbg = u->dbg;
+    a.range_flag = u->range_flag;
     a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
     if (ly.cta_group == 2) {
       a.n_row_tiles = (a.n_row_tiles + 1) & ~1;

@@ -18,5 +18,6 @@ const char* unet_op_name(const UNet* u, int i);
 const char* unet_op_kernel(const UNet* u, int i);
 int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st);
 int unet_precision(const UNet* u);
+int unet_range_status(UNet* u, int* overflow, cudaStream_t st);
 int unet_launches(const UNet* u);
 }  // namespace edmp

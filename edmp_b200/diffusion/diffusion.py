@@ -120,6 +120,7 @@ class Diffusion:
                               seed=seed, guidance_schedule=guidance_schedule, want_cost=True, condition=condition)
         self.last_final_cost = cost
         out = x.cpu().numpy()
+        model.check_range()
         return out.copy()
 
     def denoise(self, model, traj_len, num_channels, start=None, goal=None, condition=True):

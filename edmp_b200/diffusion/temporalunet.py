@@ -213,6 +213,20 @@ class TemporalUNet:
 
     __call__ = forward
 
+    def check_range(self):
+        """Raises if an activation of a forward since the last check left the IEEE-half operand range of the f16x3 /
+        f16 modes (+-65504; the results would be NaN).  Synchronises the stream; the other modes never raise."""
+        if self._handle is None:
+            return
+        flag = ctypes.c_int(0)
+        with torch.cuda.device(torch.device(self.device)):
+            _lib.check(_lib.load().edmp_unet_range_status(self._handle, ctypes.byref(flag), _lib.stream_ptr()),
+                       "edmp_unet_range_status")
+        if flag.value:
+            raise _lib.EdmpError("an activation exceeded the IEEE-half operand range (+-65504) of precision %r: the "
+                                 "output is not finite. Use precision='tf32x3' (or 'bf16x3' / 'fp32') for this "
+                                 "checkpoint." % self.precision)
+
     def read_activation(self, name, rows):
         """[rows, C, L] activation of the last forward, named like the reference module path."""
         lib = _lib.load()

@@ -87,6 +87,11 @@ const char* edmp_unet_op_kernel(const edmp_unet* u, int i);
 int edmp_unet_tc_trace(edmp_unet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas,
                        void* stream);
 int edmp_unet_precision(const edmp_unet* u);
+/* Operand-range check of the IEEE-half modes (f16x3, f16): activations are split hi + lo un-scaled, so a value beyond
+ * +-65504 would silently turn the forward into NaN.  Every epilogue raises a device flag instead; this call
+ * synchronises `stream`, reads and clears the flag: *overflow = 1 when a forward since the last call left the range
+ * (re-create the engine with tf32x3 / bf16x3 / fp32).  Always 0 for the other modes. */
+int edmp_unet_range_status(edmp_unet* u, int* overflow, void* stream);
 /* number of kernels one forward launches (for bench.py's gpu_launches claim) */
 int edmp_unet_launches_per_forward(const edmp_unet* u);
 

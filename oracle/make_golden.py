@@ -169,6 +169,102 @@ def golden_sampler():
               "nan" if np.isnan(final).any() else "finite")
 
 
+# ---- every one of the 255 steps, teacher-forced -----------------------------------------------------------------
+def _run_reference_tape(guides, bpg, scene, sd, x_T, noise, condition=True):
+    """The reference's denoise_guided with ONE intervention by the harness: the state is rounded to float32 at the entry
+    of every p_sample_using_posterior call (the network input is float32 anyway, diffusion.py:319).  Every single step
+    is then the UNMODIFIED reference step function applied to a float32-representable state, so ONE float32 tape
+    [256, B, 7, 50] holds the exact input AND (to 1e-7 relative) the reference's output of all 255 steps:
+    tape[k] = state entering step t = 255 - k, tape[k + 1] = reference output of that step."""
+    ns = ref_shim.load_reference()
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], bpg)
+    B = cfgs["total_batch_size"]
+    model = ref_shim.make_reference_unet(sd)
+    guide = ns.IntersectionVolumeGuide(obstacle_config=scene, device="cpu", guide_cfgs=cfgs, batch_size=B)
+    diff = ns.Diffusion(T=255, device="cpu")
+    ref_shim.set_noise_tape(ref_shim.NoiseTape(replay=[x_T] + list(noise)))
+    tape = np.zeros((256, B, 7, 50), dtype=np.float32)
+    post = diff.p_sample_using_posterior
+
+    def post_wrap(xt, t, eps):
+        x32 = xt.astype(np.float32)
+        tape[255 - t] = x32
+        return post(x32.astype(np.float64), t, eps)
+
+    diff.p_sample_using_posterior = post_wrap
+    devnull = open(os.devnull, "w")
+    stdout, sys.stdout = sys.stdout, devnull
+    try:
+        with np.errstate(all="ignore"):
+            final = diff.denoise_guided(model=model, guide=guide, batch_size=B, traj_len=50, num_channels=7,
+                                        condition=condition, benchmarking=True, start=scenes.START,
+                                        goal=scenes.GOAL, guidance_schedule=cfgs["guidance_schedule"])
+    finally:
+        sys.stdout = stdout
+    tape[255] = final.astype(np.float32)
+    return tape, final
+
+
+def _oracle_divergence(guides, bpg, scene, sd, x_T, noise, final_ref):
+    """per-row max |oracle chain - reference chain| at t = 0: how far the reference's OWN arithmetic, re-ordered
+    (torch fp32 restatement + autograd guide), drifts over 255 free-running steps.  The bound the GPU chain is held to
+    on the chaotic (sv / grad-norm) rows is tied to it."""
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], bpg)
+    with np.errstate(all="ignore"):
+        out = so.denoise_guided(sd, scene, cfgs, scenes.START, scenes.GOAL, x_T, noise, gradient="autograd")
+    return np.abs(out - final_ref).max(axis=(1, 2))
+
+
+TAPE_CASES = {
+    # name: (guides, rows per guide, scene, final_gain, x_T kind, x_T seed, noise seed, condition)
+    "iv": ([1, 2, 3], 2, "tabletop", 0.2, "gentle", 5, 7, True),
+    "mixed": ([1, 10, 11, 9], 1, "tabletop", 0.2, "gentle", 6, 8, True),
+    # the bench workload's ensemble and scene (bench.py build_workload), one row per guide
+    "bench10": ([1, 2, 3, 4, 5, 9, 10, 11, 12, 13], 1, "bench20", 0.2, "gentle", 100, 9, True),
+    # the chain as diffusion.py:303 draws it: x_T ~ N(0, I), un-scaled weights
+    "normal": ([1, 10, 11, 9], 1, "tabletop", 1.0, "normal", 12, 13, True),
+    # condition=False (diffusion.py:300-301,:347): the endpoints diffuse freely
+    "uncond": ([1, 10], 1, "tabletop", 0.2, "gentle", 14, 15, False),
+}
+
+
+def tape_case_inputs(name):
+    """(guides, bpg, scene, state_dict, x_T, noise list, condition) of a tape case, regenerated from its seeds."""
+    guides, bpg, scene_kind, final_gain, x_kind, xseed, nseed, condition = TAPE_CASES[name]
+    beta, alpha, abar = so.schedule()
+    if scene_kind == "tabletop":
+        scene = np.vstack([scenes.tabletop_scene(), np.array([[0.12, 0, 0.2, 0, 0, 0, 1, 0.1, 0.1, 0.1]])])
+    else:
+        scene = scenes.synthetic_scene(20, seed=1, rotated=True, cylinders=4)
+    sd = weights.seeded_state_dict(0, final_gain=final_gain)
+    B = len(guides) * bpg
+    if x_kind == "gentle":
+        x_T = scenes.gentle_x_T(B, abar[-1], seed=xseed)
+    else:
+        x_T = np.random.default_rng(xseed).normal(size=(B, 7, 50))
+    rng = np.random.default_rng(nseed)
+    noise = [rng.normal(size=(B, 7, 50)) for _ in range(255)]
+    return guides, bpg, scene, sd, x_T, noise, condition
+
+
+def golden_tapes(which=None):
+    for name in (which or TAPE_CASES):
+        guides, bpg, scene, sd, x_T, noise, condition = tape_case_inputs(name)
+        tape, final = _run_reference_tape(guides, bpg, scene, sd, x_T, noise, condition)
+        out = {"guides": np.array(guides), "bpg": bpg, "scene": scene, "condition": int(condition),
+               "tape": tape, "noise_checksum": float(sum(n.sum() for n in noise))}
+        if name in ("mixed", "bench10"):
+            # free-running drift of the reference's own arithmetic re-ordered, on the true (un-rounded) chain
+            g = np.load(os.path.join(OUT, "sampler_mixed.npz")) if name == "mixed" else None
+            final_true = g["final"] if g is not None else _run_reference_sampler(guides, bpg, scene, sd, x_T, noise, ())[0]
+            out["final_true"] = final_true
+            out["oracle_divergence"] = _oracle_divergence(guides, bpg, scene, sd, x_T, noise, final_true)
+        np.savez_compressed(os.path.join(OUT, "tape_%s.npz" % name), **out)
+        print("tape_%s.npz" % name, tape.shape, "range", float(np.nanmin(tape)), float(np.nanmax(tape)),
+              "nan" if np.isnan(tape).any() else "finite",
+              "oracle divergence %s" % np.array2string(out["oracle_divergence"], precision=2) if "oracle_divergence" in out else "")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or ["unet", "guide", "sampler"]
@@ -178,3 +274,5 @@ if __name__ == "__main__":
         golden_guide()
     if "sampler" in which:
         golden_sampler()
+    if "tapes" in which or any(w.startswith("tape:") for w in which):
+        golden_tapes([w.split(":", 1)[1] for w in which if w.startswith("tape:")] or None)

@@ -201,3 +201,33 @@ def test_metrics_oracle_matches_reference(golden):
     np.testing.assert_allclose(ex, float(g["example_sal"]), rtol=1e-12)
     # all-zero movement -> 0 (lib/metrics.py:86-88)
     assert mo.sparc(np.zeros(49), 50.)[0] == 0.0
+
+
+@pytest.mark.parametrize("case", ["iv", "mixed", "bench10", "normal", "uncond"])
+def test_oracle_single_steps_match_reference_tapes(golden, case):
+    """tests/golden/tape_<case>.npz holds all 255 steps of a reference chain (state in -> reference step -> state out,
+    oracle/make_golden.py `tapes`); the oracle restatement reproduces a spread of them (every 12th step and the last
+    five, guided and unguided, incl. t = 1 with its row-0 noise quirk) to 2e-6 rad relative to the state's size."""
+    from oracle.make_golden import TAPE_CASES, tape_case_inputs
+    g = golden("tape_%s.npz" % case)
+    guides, bpg, scene, sd, x_T, noise, condition = tape_case_inputs(case)
+    assert abs(sum(n.sum() for n in noise) - float(g["noise_checksum"])) < 1e-9
+    cfgs = so.expand_guide_tables([guide_params.GUIDES[n] for n in guides], bpg)
+    beta, alpha, abar = so.schedule()
+    tape = g["tape"].astype(np.float64)
+    assert np.array_equal(tape[0][:, :, 1:-1].astype(np.float32), x_T[:, :, 1:-1].astype(np.float32))
+    for k in sorted(set(range(0, 255, 12)) | {250, 251, 252, 253, 254}):
+        t = 255 - k
+        X = tape[k]
+        with torch.no_grad():
+            eps = unet_oracle.unet_forward(sd, torch.tensor(X, dtype=torch.float32), t).numpy()
+        X = so.posterior_step(X, t, eps, noise[k], beta, alpha, abar)
+        if t % 2 == 0 and t >= 5:
+            with np.errstate(all="ignore"):
+                G = go.gradient_analytic(so.clip_joints(X[:, :, 1:-1]), scenes.START, scenes.GOAL, scene, cfgs, t)
+            X[:, :, 1:-1] -= cfgs["guidance_schedule"][:, t - 1, None, None] * G
+        if condition:
+            X[:, :, 0], X[:, :, -1] = scenes.START, scenes.GOAL
+        scale = 2e-6 + 2e-7 * np.abs(tape[k + 1])
+        assert np.all(np.abs(X - tape[k + 1]) <= scale), "case %s step t=%d: %g" % (
+            case, t, np.max(np.abs(X - tape[k + 1]) / scale))
