@@ -19,6 +19,8 @@ class Diffusion:
     #: np.random.multivariate_normal in the reference's order (same stream as the reference under
     #: np.random.seed); "philox" draws z on the device (throughput mode).
     noise_mode = "numpy"
+    #: reverse steps per host-noise upload (numpy / recorded-tape modes)
+    NOISE_CHUNK = 16
 
     def __init__(self, T, device, variance_thresh=0.02):
         self.T = T
@@ -99,15 +101,11 @@ class Diffusion:
         dev = _lib.require_cuda(self.device)
         B = int(batch_size)
         mode = noise if noise is not None else self.noise_mode
-        tape = None
+        zs = None
         if isinstance(mode, (tuple, list)):
             x_T, zs = mode
             x_T = np.asarray(x_T, dtype=np.float64)
-            tape = np.stack([np.asarray(z, dtype=np.float64) for z in zs])
-        elif mode == "numpy":
-            x_T = self._draw(traj_len, (B, num_channels))
-            tape = np.stack([self._draw(traj_len, (B, num_channels)) for _ in range(self.T)])
-        elif mode == "philox":
+        elif mode in ("numpy", "philox"):
             x_T = self._draw(traj_len, (B, num_channels))
         else:
             raise ValueError("unknown noise mode %r" % (mode,))
@@ -115,9 +113,25 @@ class Diffusion:
             seed = int(np.random.randint(0, 2 ** 31 - 1)) if mode == "philox" else 0
         model.train(False)
         x = torch.as_tensor(x_T, dtype=torch.float64).to(dev).contiguous()
-        z = torch.as_tensor(tape).to(dev).contiguous() if tape is not None else None
-        cost = self.run_steps(model, guide, x, np.asarray(start)[:], np.asarray(goal)[:], self.T, 0, noise=z,
-                              seed=seed, guidance_schedule=guidance_schedule, want_cost=True, condition=condition)
+        start, goal = np.asarray(start)[:], np.asarray(goal)[:]
+        if mode == "philox":
+            cost = self.run_steps(model, guide, x, start, goal, self.T, 0, noise=None, seed=seed,
+                                  guidance_schedule=guidance_schedule, want_cost=True, condition=condition)
+        else:
+            # Host noise (the reference's np.random stream, or a recorded tape) reaches the device in chunks of
+            # NOISE_CHUNK steps: the draws of the next chunk overlap the kernels of the current one, and an 8190-row
+            # pass never holds more than 16 x 23 MB of noise instead of the whole 5.9 GB tape.
+            cost, t = None, self.T
+            while t > 0:
+                n = min(self.NOISE_CHUNK, t)
+                if zs is not None:
+                    chunk = np.stack([np.asarray(z, dtype=np.float64) for z in zs[self.T - t:self.T - t + n]])
+                else:
+                    chunk = np.stack([self._draw(traj_len, (B, num_channels)) for _ in range(n)])
+                z = torch.as_tensor(chunk).to(dev).contiguous()
+                cost = self.run_steps(model, guide, x, start, goal, t, t - n, noise=z, seed=seed,
+                                      guidance_schedule=guidance_schedule, want_cost=(t - n == 0), condition=condition)
+                t -= n
         self.last_final_cost = cost
         out = x.cpu().numpy()
         model.check_range()

@@ -74,7 +74,7 @@ def quat_xyzw_to_matrix(q):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
-def obstacle_aabbs(obstacle_config, expansion_t=None, clearance_t=None, rows=1):
+def obstacle_aabbs(obstacle_config, expansion_t=None, clearance_t=None, rows=1, device="cpu"):
     """obs_min/obs_max [rows, no, 3] float32 as define_obstacles (:118-158) builds them.
     expansion_t / clearance_t: [rows] values at index t-1, or None for t == 0."""
     cfg = np.asarray(obstacle_config, dtype=np.float64)
@@ -83,22 +83,22 @@ def obstacle_aabbs(obstacle_config, expansion_t=None, clearance_t=None, rows=1):
     if expansion_t is not None:
         sizes = np.maximum(sizes, np.asarray(expansion_t, dtype=np.float64)[:, None, None])
         sizes = sizes + np.asarray(clearance_t, dtype=np.float64)[:, None, None]
-    half = torch.tensor(sizes, dtype=torch.float32) / 2            # [rows,no,3]
-    verts = torch.ones(rows, no, 4, 8, dtype=torch.float32)
-    verts[:, :, :3, :] = half[:, :, :, None] * torch.tensor(BOX_SIGNS, dtype=torch.float32)
+    half = torch.tensor(sizes, dtype=torch.float32, device=device) / 2            # [rows,no,3]
+    verts = torch.ones(rows, no, 4, 8, dtype=torch.float32, device=device)
+    verts[:, :, :3, :] = half[:, :, :, None] * torch.tensor(BOX_SIGNS, dtype=torch.float32, device=device)
     T = np.zeros((no, 4, 4))
     for i in range(no):
         T[i, :3, :3] = quat_xyzw_to_matrix(cfg[i, 3:7])
         T[i, :3, 3] = cfg[i, :3]
     T[:, 3, 3] = 1.0
-    T = torch.tensor(T, dtype=torch.float32)[None].expand(rows, no, 4, 4)
+    T = torch.tensor(T, dtype=torch.float32, device=device)[None].expand(rows, no, 4, 4)
     wv = torch.matmul(T, verts)
     return wv.min(dim=-1)[0][:, :, :3], wv.max(dim=-1)[0][:, :, :3]
 
 
 def _dh_matrix_torch(a, d, alpha, q):
     """[...,4,4] float32 from broadcastable a,d,alpha,q tensors (get_tf_mat :45-72)."""
-    T = torch.zeros(q.shape + (4, 4), dtype=torch.float32)
+    T = torch.zeros(q.shape + (4, 4), dtype=torch.float32, device=q.device)
     ca, sa = torch.cos(alpha), torch.sin(alpha)
     cq, sq = torch.cos(q), torch.sin(q)
     T[..., 0, 0] = cq
@@ -118,9 +118,10 @@ def _dh_matrix_torch(a, d, alpha, q):
 
 def link_aabbs_torch(joints, link_dims=LINK_DIMS):
     """joints [B,n,7] float32 tensor -> (link_min, link_max) [B,n,9,3]  (:74-98, :344-375)."""
-    dh = torch.tensor(DH, dtype=torch.float32)
+    dev = joints.device
+    dh = torch.tensor(DH, dtype=torch.float32, device=dev)
     B, n, _ = joints.shape
-    T = torch.eye(4, dtype=torch.float32).expand(B, n, 4, 4)
+    T = torch.eye(4, dtype=torch.float32, device=dev).expand(B, n, 4, 4)
     frames = []
     for i in range(7):
         M = _dh_matrix_torch(dh[i, 0].expand(B, n), dh[i, 1].expand(B, n), dh[i, 2].expand(B, n),
@@ -128,10 +129,10 @@ def link_aabbs_torch(joints, link_dims=LINK_DIMS):
         T = torch.matmul(T, M)
         frames.append(T)
     fk = torch.stack([frames[j] for j in LINK_JOINT], dim=2)              # [B,n,9,4,4]
-    link_T = fk @ torch.tensor(static_frames(), dtype=torch.float32)
-    ld = torch.tensor(np.asarray(link_dims), dtype=torch.float32)
-    verts = torch.ones(9, 4, 8, dtype=torch.float32)
-    verts[:, :3, :] = (ld / 2)[:, :, None] * torch.tensor(BOX_SIGNS, dtype=torch.float32)
+    link_T = fk @ torch.tensor(static_frames(), dtype=torch.float32, device=dev)
+    ld = torch.tensor(np.asarray(link_dims), dtype=torch.float32, device=dev)
+    verts = torch.ones(9, 4, 8, dtype=torch.float32, device=dev)
+    verts[:, :3, :] = (ld / 2)[:, :, None] * torch.tensor(BOX_SIGNS, dtype=torch.float32, device=dev)
     wv = (link_T @ verts)[:, :, :, :3, :]
     return wv.min(dim=-1)[0], wv.max(dim=-1)[0]
 
@@ -155,8 +156,8 @@ def sv_cost(joint_input, start, goal, omin, omax, link_dims=LINK_DIMS):
     """swept_volume_cost() :473-537 (start/goal padded, consecutive AABBs unioned)."""
     q = joint_input.permute(0, 2, 1)
     B = q.shape[0]
-    s = torch.as_tensor(start, dtype=torch.float32).reshape(1, 1, 7).expand(B, 1, 7)
-    g = torch.as_tensor(goal, dtype=torch.float32)
+    s = torch.as_tensor(start, dtype=torch.float32).to(q.device).reshape(1, 1, 7).expand(B, 1, 7)
+    g = torch.as_tensor(goal, dtype=torch.float32).to(q.device)
     g = g.reshape(1, 1, 7).expand(B, 1, 7) if g.numel() == 7 else g.reshape(B, 1, 7)
     traj = torch.cat([s, q, g], dim=1)
     lmin, lmax = link_aabbs_torch(traj, link_dims)
@@ -174,17 +175,18 @@ def mix_grad_norm(G32, grad_norm):
 
 
 def gradient_autograd(joint_input, start, goal, obstacle_config, guide_cfgs, t,
-                      link_dims=LINK_DIMS, raw=False):
-    """get_gradient :597-635 restated: float32 autograd of sum((1-m)*iv) + sum(m*sv)."""
+                      link_dims=LINK_DIMS, raw=False, device="cpu"):
+    """get_gradient :597-635 restated: float32 autograd of sum((1-m)*iv) + sum(m*sv).  (``device``: where the torch
+    ops run -- the tests use the CPU; bench.py's secondary baseline runs the same restatement on cuda.)"""
     B = joint_input.shape[0]
-    q = torch.tensor(np.asarray(joint_input), dtype=torch.float32, requires_grad=True)
+    q = torch.tensor(np.asarray(joint_input), dtype=torch.float32, device=device, requires_grad=True)
     omin, omax = obstacle_aabbs(obstacle_config, guide_cfgs["expansion"][:, t - 1],
-                                guide_cfgs["clearance"][:, t - 1], rows=B)
-    m = torch.tensor(guide_cfgs["guidance_method"], dtype=torch.float32).view(B, 1, 1)
+                                guide_cfgs["clearance"][:, t - 1], rows=B, device=device)
+    m = torch.tensor(guide_cfgs["guidance_method"], dtype=torch.float32, device=device).view(B, 1, 1)
     cost = torch.sum((1 - m) * iv_cost(q, omin, omax, link_dims)) + \
         torch.sum(m * sv_cost(q, start, goal, omin, omax, link_dims))
     cost.backward()
-    G = q.grad.numpy()
+    G = q.grad.cpu().numpy()
     return G if raw else mix_grad_norm(G, guide_cfgs["grad_norm"])
 
 

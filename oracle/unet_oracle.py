@@ -16,7 +16,7 @@ def time_embedding(sd, t):
     """t: float tensor [1] -> [1, 32]   (blocks.py:44-54, :83-88)"""
     half = 16
     scale = math.log(10000) / (half - 1)
-    freqs = torch.exp(torch.arange(half) * -scale)
+    freqs = torch.exp(torch.arange(half) * -scale).to(t.device)
     ang = t[:, None] * freqs[None, :]
     emb = torch.cat((ang.sin(), ang.cos()), dim=-1)
     h = F.linear(emb, sd["time_embedding.time_mlp.1.weight"], sd["time_embedding.time_mlp.1.bias"])
@@ -52,7 +52,8 @@ def unet_forward(sd, x, t, taps=None):
     ``taps`` (dict) optionally receives every block output for per-layer parity."""
     if not torch.is_tensor(t):
         t = torch.tensor([float(t)], dtype=torch.float32)
-    temb = time_embedding(sd, t.to(torch.float32))
+    # (device-agnostic: bench.py's secondary baseline runs this same restatement on cuda with stock PyTorch kernels)
+    temb = time_embedding(sd, t.to(x.device, torch.float32))
     n_down = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("down_samplers."))
     n_up = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("up_samplers."))
     skips = []

@@ -347,7 +347,7 @@ def test_sampler_end_to_end_iv(golden, model02):
 def test_sampler_end_to_end_mixed_reports(golden, model02):
     """iv+sv+grad-norm ensemble.  The chain is chaotic for sv rows (the reference's own arithmetic
     re-ordered diverges by ~0.1 rad), so only the iv row is held to 1e-4; the rest must
-    stay finite and close in the loose sense."""
+    stay finite and within 10x of the reference's own re-ordered drift."""
     from edmp_b200 import Diffusion, IntersectionVolumeGuide
     g, cfgs, noise = _replay(golden, "mixed")
     B = cfgs["total_batch_size"]
@@ -359,7 +359,13 @@ def test_sampler_end_to_end_mixed_reports(golden, model02):
     print("e2e mixed [%s] per-row max error (rad):" % model02.precision, err)
     assert np.isfinite(out).all()
     assert err[0] <= E2E_TOL[model02.precision]
-    assert err.max() <= 1.0
+    # the chaotic rows: within 10x of how far the reference's own arithmetic, re-ordered, drifts on this very chain
+    # (8.6e-2 / 9.7e-3 / 3.2e-3 rad, measured by oracle/make_golden.py and stored next to the all-steps tape)
+    drift = golden("tape_mixed.npz")["oracle_divergence"]
+    if model02.precision in ("fp32", "tf32x3", "f16x3"):
+        assert np.all(err <= np.maximum(E2E_TOL[model02.precision], 10.0 * drift)), (err, drift)
+    else:
+        assert err.max() <= 1.0
 
 
 def test_sampler_properties_full_batch(model02):

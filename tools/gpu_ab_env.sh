@@ -4,7 +4,7 @@ TAG=$1; VAR=$2; shift 2
 mkdir -p gpurun_out
 for V in "$@"; do
   if [ "$V" = "-" ]; then unset $VAR; else export $VAR=$V; fi
-  timeout 600 python bench.py --no-cpu-baseline --steps 2 --ops-out gpurun_out/${TAG}_${V}_ops.txt > gpurun_out/${TAG}_${V}.json 2> gpurun_out/${TAG}_${V}.err
+  timeout 600 python bench.py --quick --steps 2 --ops-out gpurun_out/${TAG}_${V}_ops.txt > gpurun_out/${TAG}_${V}.json 2> gpurun_out/${TAG}_${V}.err
   python -c "
 import json
 d=json.load(open('gpurun_out/${TAG}_${V}.json'))

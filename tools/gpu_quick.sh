@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 EDMP_TEST_PRECISIONS=$PREC timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log
 tail -12 gpurun_out/${TAG}_tests.log
 for RPG in 102 819; do
-  timeout 900 python bench.py --precision $PREC --rows-per-guide $RPG --no-cpu-baseline --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
+  timeout 900 python bench.py --precision $PREC --rows-per-guide $RPG --quick --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/${TAG}_bench_${RPG}.json'))

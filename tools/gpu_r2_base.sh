@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --for
 timeout 300 python tools/tc_trace.py 1020 $PREC > gpurun_out/${TAG}_trace_1020.txt 2>&1
 timeout 300 python tools/tc_trace.py 8190 $PREC > gpurun_out/${TAG}_trace_8190.txt 2>&1
 for RPG in 102 819; do
-  timeout 600 python bench.py --precision $PREC --rows-per-guide $RPG --no-cpu-baseline --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
+  timeout 600 python bench.py --precision $PREC --rows-per-guide $RPG --quick --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/${TAG}_bench_${RPG}.json'))

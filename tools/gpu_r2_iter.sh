@@ -7,7 +7,7 @@ EDMP_TEST_PRECISIONS=$PREC timeout 900 python -m pytest tests -m gpu -x -q -k "$
 tail -15 gpurun_out/${TAG}_tests.log
 timeout 300 python tools/tc_trace.py 1020 $PREC > gpurun_out/${TAG}_trace_1020.txt 2>&1
 for RPG in $RPGS; do
-  timeout 600 python bench.py --precision $PREC --rows-per-guide $RPG --no-cpu-baseline --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
+  timeout 600 python bench.py --precision $PREC --rows-per-guide $RPG --quick --steps 2 --ops-out gpurun_out/${TAG}_ops_${RPG}.txt > gpurun_out/${TAG}_bench_${RPG}.json 2> gpurun_out/${TAG}_bench_${RPG}.err
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/${TAG}_bench_${RPG}.json'))
