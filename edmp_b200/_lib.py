@@ -19,6 +19,11 @@ SIGNATURES = {
     "edmp_unet_param_count": (c_size_t, [P(c_int), c_int]),
     "edmp_unet_create": (c_int, [c_void_p, c_size_t, P(c_int), c_int, c_int, c_int, P(c_void_p)]),
     "edmp_unet_destroy": (None, [c_void_p]),
+    "edmp_unet_pack": (c_int, [c_void_p, c_size_t, P(c_int), c_int, c_int, c_int, P(c_void_p)]),
+    "edmp_unet_blob_bytes": (c_size_t, [c_void_p]),
+    "edmp_unet_blob_read": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "edmp_unet_create_from_blob": (c_int, [c_void_p, c_size_t, c_int, P(c_void_p)]),
+    "edmp_unet_blob_layout_version": (c_int, []),
     "edmp_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "edmp_unet_read_activation": (c_int, [c_void_p, c_char_p, c_int, c_void_p, P(c_int), P(c_int), c_void_p]),
     "edmp_unet_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -82,6 +82,33 @@ int edmp_unet_create(const float* params_h, size_t n_params, const int* dims, in
   } catch (const std::exception& e) { set_error(std::string("edmp: exception: ") + e.what()); return 3; }
 }
 void edmp_unet_destroy(edmp_unet* u) { if (u) { unet_destroy(u->impl); delete u; } }
+int edmp_unet_pack(const float* params_h, size_t n_params, const int* dims, int n_dims, int precision, int max_rows,
+                   edmp_unet** out) {
+  if (!params_h || !dims || !out) { set_error("edmp_unet_pack: null argument"); return 2; }
+  try {
+    UNet* u = nullptr;
+    int rc = unet_pack(params_h, n_params, dims, n_dims, precision, max_rows, &u);
+    if (rc) return rc;
+    *out = new edmp_unet{u};
+    return 0;
+  } catch (const std::exception& e) { set_error(std::string("edmp: exception: ") + e.what()); return 3; }
+}
+size_t edmp_unet_blob_bytes(const edmp_unet* u) { return u ? unet_blob_bytes(u->impl) : 0; }
+int edmp_unet_blob_read(edmp_unet* u, void* dst_h, size_t capacity) {
+  if (!u || !dst_h) { set_error("edmp_unet_blob_read: null argument"); return 2; }
+  EDMP_TRY(unet_blob_read(u->impl, dst_h, capacity));
+}
+int edmp_unet_create_from_blob(const void* blob_h, size_t nbytes, int max_rows, edmp_unet** out) {
+  if (!blob_h || !out) { set_error("edmp_unet_create_from_blob: null argument"); return 2; }
+  try {
+    UNet* u = nullptr;
+    int rc = unet_create_from_blob(blob_h, nbytes, max_rows, &u);
+    if (rc) return rc;
+    *out = new edmp_unet{u};
+    return 0;
+  } catch (const std::exception& e) { set_error(std::string("edmp: exception: ") + e.what()); return 3; }
+}
+int edmp_unet_blob_layout_version(void) { return unet_blob_layout_version(); }
 int edmp_unet_forward(edmp_unet* u, const float* x_d, int t, int rows, float* eps_d, void* stream) {
   if (!u || !x_d || !eps_d) { set_error("edmp_unet_forward: null argument"); return 2; }
   EDMP_TRY(unet_forward(u->impl, x_d, t, rows, eps_d, (cudaStream_t)stream));

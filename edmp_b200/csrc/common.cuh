@@ -5,9 +5,20 @@
 #include <cstdio>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a no-op unless a profiler (nsys / ncu --nvtx) is attached
+
 namespace edmp {
 
 void set_error(const std::string& msg);
+
+// NVTX range for the lifetime of the object: the sampler marks every pass and every reverse step, the UNet every
+// forward (SURVEY.md section 5 "tracing"); `ncu --nvtx --nvtx-include "step t=254/"` then profiles one step.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define EDMP_CK(call)                                                                       \
   do {                                                                                      \

@@ -130,6 +130,9 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
   for (int j = 0; j < 7; ++j) { sc.start[j] = start[j]; sc.goal[j] = goal[j]; }
   sc.c1 = sc.sqrt_alpha = sc.beta = 0.0;
   long long launches = 0;
+  char label[96];
+  snprintf(label, sizeof(label), "edmp_sample_guided rows=%d t=%d..%d%s", rows, t_start, t_stop + 1, scene ? " guided" : "");
+  NvtxRange pass_range(label);
   // one fused launch per step after the UNet (posterior, gradient, norm mix, guided update); EDMP_SPLIT_TAIL=1 keeps the
   // three separate kernels (A/B, and the unguided path always uses posterior_kernel)
   static const bool split_tail = getenv("EDMP_SPLIT_TAIL") != nullptr;
@@ -139,6 +142,8 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
   condition_kernel<<<blocks, threads, 0, st>>>(x, s->xf, sc, s->condition, n);
   ++launches;
   for (int t = t_start; t > t_stop; --t) {
+    snprintf(label, sizeof(label), "step t=%d%s", t, (scene && (t % 2) == 0 && t >= 5) ? " (guided)" : "");
+    NvtxRange step_range(label);
     if (unet_forward(u, s->xf, t, rows, s->eps, st)) return 1;
     launches += unet_launches(u);
     const double a = s->alpha[t - 1], ab = s->alpha_bar[t - 1];

@@ -245,6 +245,14 @@ struct UNet {
   int cpc() const { return tc_16() ? 64 : 32; }   // channels per 128-byte K chunk
   long long* dbg = nullptr;  // clock stamps of tensor-core CTAs (debug)
   unsigned* range_flag = nullptr;   // device flag: an activation left the IEEE-half operand range (f16x3 / f16 modes)
+  // Packed-weight blob: every device image this engine uploads -- repacked weight tiles,
+  // per-channel vectors, the time-embedding table -- in creation order, each item tagged with the tile geometry it was
+  // packed for.  `rec`: being recorded while the engine is built from a state_dict; `play`: the engine is built FROM a
+  // blob (no parameters, no repacking: items are uploaded as they are, sizes and tags must match the plan).
+  std::vector<uint8_t>* rec = nullptr;
+  const uint8_t* play = nullptr;
+  size_t play_bytes = 0, play_pos = 0;
+  bool play_bad = false;
   int max_rows = 0;
   int n_launches = 0;
   std::vector<void*> dev_allocs;
@@ -258,7 +266,40 @@ struct UNet {
   int final_c = 0;
 };
 
-static void* upload_bytes(UNet* u, const void* data, size_t bytes) {
+constexpr uint32_t kBlobLayoutVersion = 3;        // bump whenever a packed layout, the item order or a tag changes
+struct BlobHeader {
+  char magic[8];                                  // "EDMPBLOB"
+  uint32_t version, precision, n_dims, dims[8], max_rows;
+  uint64_t n_params;
+};
+struct BlobItem { uint64_t bytes, tag; };
+
+static void blob_append(std::vector<uint8_t>& v, const void* data, size_t bytes) {
+  const uint8_t* b = static_cast<const uint8_t*>(data);
+  v.insert(v.end(), b, b + bytes);
+  v.resize((v.size() + 15) & ~(size_t)15, 0);
+}
+// next item of the blob being played: its payload, or null (and play_bad) when it is not what the plan asks for
+static const uint8_t* blob_next(UNet* u, size_t bytes, uint64_t tag) {
+  BlobItem it;
+  if (u->play_bad || u->play_pos + sizeof(it) > u->play_bytes) { u->play_bad = true; return nullptr; }
+  std::memcpy(&it, u->play + u->play_pos, sizeof(it));
+  const size_t payload = u->play_pos + sizeof(it);
+  if (it.bytes != bytes || it.tag != tag || payload + bytes > u->play_bytes) { u->play_bad = true; return nullptr; }
+  u->play_pos = (payload + bytes + 15) & ~(size_t)15;
+  return u->play + payload;
+}
+
+// device copy of a packed image; recorded into / served from the blob (`tag`: geometry the image was packed for)
+static void* upload_bytes(UNet* u, const void* data, size_t bytes, uint64_t tag = 0) {
+  if (u->play) {
+    data = blob_next(u, bytes, tag);
+    if (!data) return nullptr;
+  } else if (u->rec) {
+    BlobItem it{bytes, tag};
+    blob_append(*u->rec, &it, sizeof(it));
+    blob_append(*u->rec, data, bytes);
+  }
   void* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
   if (cudaMemcpy(p, data, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -267,6 +308,20 @@ static void* upload_bytes(UNet* u, const void* data, size_t bytes) {
   }
   u->dev_allocs.push_back(p);
   return p;
+}
+// a host-side scalar of the plan that depends on the weights (the power-of-two scale of a packed tile)
+static void blob_scalar(UNet* u, float* v) {
+  if (u->play) {
+    const uint8_t* src = blob_next(u, sizeof(float), 0x5CA1E);
+    if (src) std::memcpy(v, src, sizeof(float));
+  } else if (u->rec) {
+    BlobItem it{sizeof(float), 0x5CA1E};
+    blob_append(*u->rec, &it, sizeof(it));
+    blob_append(*u->rec, v, sizeof(float));
+  }
+}
+static uint64_t geom_tag(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e) {
+  return ((((a * 1315423911ull + b) * 1315423911ull + c) * 1315423911ull + d) * 1315423911ull + e) | (1ull << 63);
 }
 static float* upload(UNet* u, const std::vector<float>& v) {
   return static_cast<float*>(upload_bytes(u, v.data(), v.size() * sizeof(float)));
@@ -332,12 +387,15 @@ struct Builder {
   bool ok = true;
   std::string why;            // which plan check failed (for the error message)
 
-  const float* P(const std::string& name) const { return params + pw->table.at(name).off; }
+  // (null while the engine is built from a blob: nothing below may read parameters then)
+  const float* P(const std::string& name) const { return params ? params + pw->table.at(name).off : nullptr; }
+  bool playing() const { return u->play != nullptr; }
 
   // conv weight [cout][cin][k] -> [cin][k][cout]
   float* pack_conv(const std::string& name, int cout, int cin, int k) {
     const float* w = P(name);
     std::vector<float> v((size_t)cin * k * cout);
+    if (!playing())
     for (int co = 0; co < cout; ++co)
       for (int ci = 0; ci < cin; ++ci)
         for (int t = 0; t < k; ++t) v[((size_t)ci * k + t) * cout + co] = w[((size_t)co * cin + ci) * k + t];
@@ -349,6 +407,7 @@ struct Builder {
   float* pack_convT(const std::string& name, int cin, int cout, int k) {
     const float* w = P(name);
     std::vector<float> v((size_t)cin * k * cout);
+    if (!playing())
     for (int ci = 0; ci < cin; ++ci)
       for (int co = 0; co < cout; ++co)
         for (int t = 0; t < k; ++t) v[((size_t)ci * k + t) * cout + co] = w[((size_t)ci * cout + co) * k + t];
@@ -357,7 +416,8 @@ struct Builder {
     return p;
   }
   float* vec(const std::string& name, int n) {
-    std::vector<float> v(P(name), P(name) + n);
+    std::vector<float> v((size_t)n);
+    if (!playing()) std::copy(P(name), P(name) + n, v.begin());
     float* p = upload(u, v);
     ok = ok && p;
     return p;
@@ -445,6 +505,15 @@ struct Builder {
                float* acc_scale, int halves = 1) {
     const int cpc = u->cpc(), ebytes = u->tc_16() ? 2 : 4, epc = 16 / ebytes;
     const int n_tiles = cout / ct, kch = cin / cpc;
+    const uint64_t tag = geom_tag(cout, cin, ct, slots, halves);
+    if (playing()) {
+      const size_t bytes = (size_t)slots * ct * 128 * n_tiles * kch;
+      blob_scalar(u, acc_scale);
+      *hi_out = upload_bytes(u, nullptr, bytes, tag);
+      *lo_out = u->tc_split ? upload_bytes(u, nullptr, bytes, tag) : nullptr;
+      ok = ok && *hi_out && (!u->tc_split || *lo_out);
+      return;
+    }
     float scale = 1.0f;
     if (u->tc_el == TC_EL_F16) {
       float wmax = 0.0f;
@@ -457,6 +526,7 @@ struct Builder {
       scale = std::ldexp(1.0f, e);
     }
     *acc_scale = 1.0f / scale;
+    blob_scalar(u, acc_scale);
     const size_t tile = (size_t)slots * ct * 128;   // bytes
     std::vector<uint8_t> hi(tile * n_tiles * kch), lo(u->tc_split ? hi.size() : 0);
     for (int nt = 0; nt < n_tiles; ++nt)
@@ -496,11 +566,11 @@ struct Builder {
             }
           }
       }
-    *hi_out = upload_bytes(u, hi.data(), hi.size());
+    *hi_out = upload_bytes(u, hi.data(), hi.size(), tag);
     ok = ok && *hi_out;
     *lo_out = nullptr;
     if (u->tc_split) {
-      *lo_out = upload_bytes(u, lo.data(), lo.size());
+      *lo_out = upload_bytes(u, lo.data(), lo.size(), tag);
       ok = ok && *lo_out;
     }
   }
@@ -895,17 +965,21 @@ struct Builder {
     std::vector<uint8_t> hi((size_t)n_slots * nkc * cout * rby), lo(hi.size());
     const float* w = P(p + ".block.0.weight");   // [cout][cin_real][5]; the packed input has C >= cin_real channels
     const int cin_real = pw->table.at(p + ".block.0.weight").d1;
-    t.acc_scale = pack_pm_slots(hi, lo, 0, 5, n_slots, cout, C, nkc, [&](int co, int ci, int sl) {
-      return ci < cin_real ? w[((size_t)co * cin_real + ci) * 5 + sl] : 0.0f;
-    });
+    if (!playing())
+      t.acc_scale = pack_pm_slots(hi, lo, 0, 5, n_slots, cout, C, nkc, [&](int co, int ci, int sl) {
+        return ci < cin_real ? w[((size_t)co * cin_real + ci) * 5 + sl] : 0.0f;
+      });
+    blob_scalar(u, &t.acc_scale);
     if (aux) {
       const float* wr = P(aux_prefix + ".residual_conv.weight");   // [cout][cin_real][1]
       t.aux = 1;
       t.terms[5].acc = 1; t.terms[5].slot = 5; t.terms[5].off = 2;
       t.n_terms = 6;
-      t.aux_scale = pack_pm_slots(hi, lo, 5, 1, n_slots, cout, C, nkc, [&](int co, int ci, int) {
-        return ci < cin_real ? wr[(size_t)co * cin_real + ci] : 0.0f;
-      });
+      if (!playing())
+        t.aux_scale = pack_pm_slots(hi, lo, 5, 1, n_slots, cout, C, nkc, [&](int co, int ci, int) {
+          return ci < cin_real ? wr[(size_t)co * cin_real + ci] : 0.0f;
+        });
+      blob_scalar(u, &t.aux_scale);
       t.aux_bias = vec(aux_prefix + ".residual_conv.bias", cout);
       *aux_out = new_act(u, aux_prefix + ".residual_conv", cout, L, false, false, true);
       ok = ok && aux_out->ok;
@@ -913,8 +987,9 @@ struct Builder {
       t.aux_lo = aux_out->plo;
     }
     (void)cin;
-    t.w_hi = upload_bytes(u, hi.data(), hi.size());
-    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size()) : nullptr;
+    const uint64_t wtag = geom_tag(n_slots, cout, C, nkc, u->pm2 ? cout : kPmCt);
+    t.w_hi = upload_bytes(u, hi.data(), hi.size(), wtag);
+    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size(), wtag) : nullptr;
     ok = ok && t.w_hi && (!u->tc_split || t.w_lo);
     t.bias = vec(p + ".block.0.bias", cout);
     t.gamma = vec(p + ".block.2.weight", cout);
@@ -982,11 +1057,14 @@ struct Builder {
       atoms_needed = 16 * ((L + 15) / 16) + 4;
     }
     std::vector<uint8_t> hi((size_t)n_slots * C * rby), lo(hi.size());
-    t.acc_scale = pack_pm_slots(hi, lo, 0, n_slots, n_slots, C, C, 1, [&](int co, int ci, int sl) {
-      return up ? w[((size_t)ci * C + co) * 4 + sl] : w[((size_t)co * C + ci) * 3 + sl];
-    });
-    t.w_hi = upload_bytes(u, hi.data(), hi.size());
-    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size()) : nullptr;
+    if (!playing())
+      t.acc_scale = pack_pm_slots(hi, lo, 0, n_slots, n_slots, C, C, 1, [&](int co, int ci, int sl) {
+        return up ? w[((size_t)ci * C + co) * 4 + sl] : w[((size_t)co * C + ci) * 3 + sl];
+      });
+    blob_scalar(u, &t.acc_scale);
+    const uint64_t wtag = geom_tag(n_slots, C, C, up ? 2 : 1, u->pm2 ? C : kPmCt);
+    t.w_hi = upload_bytes(u, hi.data(), hi.size(), wtag);
+    t.w_lo = u->tc_split ? upload_bytes(u, lo.data(), lo.size(), wtag) : nullptr;
     ok = ok && t.w_hi && (!u->tc_split || t.w_lo);
     t.bias = vec(name + ".bias", C);
     if (tc_out) { t.tc_hi = y.thi; t.tc_lo = y.tlo; }
@@ -1051,8 +1129,10 @@ struct Builder {
   }
 };
 
-int unet_create(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
-                int max_rows, UNet** out) {
+// params != null: build from a state_dict (record != 0: keep the packed blob, unet_blob_*); params == null: build from
+// `blob` (made by an earlier recording with the same dims / precision / layout version and a matching plan)
+static int unet_create_impl(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
+                            int max_rows, const void* blob, size_t blob_bytes, bool record, UNet** out) {
   EDMP_REQUIRE(n_dims == 6 && dims[0] == 32 && dims[1] == 64 && dims[2] == 128 && dims[3] == 256 &&
                    dims[4] == 512 && dims[5] == 512,
                "only dims=(32,64,128,256,512,512) is compiled in (infer_serial.py:50)");
@@ -1062,10 +1142,25 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   ParamWalker pw;
   walk_params(dims, n_dims, pw);
   EDMP_REQUIRE(pw.cursor == n_params, "parameter count does not match the state_dict layout");
+  EDMP_REQUIRE((params != nullptr) != (blob != nullptr), "either a state_dict or a packed blob");
 
   UNet* u = new UNet();
   u->precision = precision;
   u->max_rows = max_rows;
+  if (blob) {
+    u->play = static_cast<const uint8_t*>(blob);
+    u->play_bytes = blob_bytes;
+    u->play_pos = (sizeof(BlobHeader) + 15) & ~(size_t)15;
+  } else if (record) {
+    u->rec = new std::vector<uint8_t>();
+    BlobHeader h;
+    std::memset(&h, 0, sizeof(h));
+    std::memcpy(h.magic, "EDMPBLOB", 8);
+    h.version = kBlobLayoutVersion; h.precision = (uint32_t)precision; h.n_dims = (uint32_t)n_dims;
+    for (int i = 0; i < n_dims; ++i) h.dims[i] = (uint32_t)dims[i];
+    h.max_rows = (uint32_t)max_rows; h.n_params = n_params;
+    blob_append(*u->rec, &h, sizeof(h));
+  }
   u->tc = precision != EDMP_PRECISION_FP32;
   u->tc_split = precision == EDMP_PRECISION_TF32X3 || precision == EDMP_PRECISION_BF16X3 ||
                 precision == EDMP_PRECISION_F16X3;
@@ -1201,7 +1296,7 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   u->temb_width = b.temb_width;
   std::vector<float> table((size_t)kTSteps * b.temb_width);
   const double freq_scale = std::log(10000.0) / (16 - 1);
-  for (int t = 1; t <= kTSteps; ++t) {
+  for (int t = 1; t <= kTSteps && !b.playing(); ++t) {
     float emb[32], h1[128], te[32], mte[32];
     for (int i = 0; i < 16; ++i) {
       const float f = expf((float)i * (float)(-freq_scale));
@@ -1221,11 +1316,18 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
   }
   u->temb = upload(u, table);
   b.ok = b.ok && u->temb;
+  if (u->play && (u->play_bad || u->play_pos != ((u->play_bytes + 15) & ~(size_t)15))) {
+    set_error("unet_create_from_blob: the blob does not match this engine's plan (packed for another batch-size class, "
+              "kernel generation or layout): repack from the state_dict");
+    unet_destroy(u);
+    return 4;
+  }
   if (!b.ok) {
     set_error("unet_create: allocation failed or an unsupported layer shape was requested:" + b.why);
     unet_destroy(u);
     return 1;
   }
+  u->play = nullptr;
   u->n_launches = (int)u->layers.size() + (u->final_fused ? 0 : 1);
   *out = u;
   return 0;
@@ -1234,7 +1336,48 @@ int unet_create(const float* params, size_t n_params, const int* dims, int n_dim
 void unet_destroy(UNet* u) {
   if (!u) return;
   for (void* p : u->dev_allocs) cudaFree(p);
+  delete u->rec;
   delete u;
+}
+
+int unet_create(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
+                int max_rows, UNet** out) {
+  return unet_create_impl(params, n_params, dims, n_dims, precision, max_rows, nullptr, 0, false, out);
+}
+
+// checkpoint -> engine + packed blob (reference temporalunet.py:78-92 is the checkpoint side)
+int unet_pack(const float* params, size_t n_params, const int* dims, int n_dims, int precision, int max_rows,
+              UNet** out) {
+  return unet_create_impl(params, n_params, dims, n_dims, precision, max_rows, nullptr, 0, true, out);
+}
+
+int unet_blob_layout_version() { return (int)kBlobLayoutVersion; }
+size_t unet_blob_bytes(const UNet* u) { return u->rec ? u->rec->size() : 0; }
+
+// copies the recorded blob out and releases the host copy
+int unet_blob_read(UNet* u, void* dst, size_t cap) {
+  EDMP_REQUIRE(u->rec != nullptr, "this engine holds no packed blob (create it with edmp_unet_pack)");
+  EDMP_REQUIRE(cap >= u->rec->size(), "destination too small for the packed blob");
+  std::memcpy(dst, u->rec->data(), u->rec->size());
+  delete u->rec;
+  u->rec = nullptr;
+  return 0;
+}
+
+int unet_create_from_blob(const void* blob, size_t bytes, int max_rows, UNet** out) {
+  EDMP_REQUIRE(blob != nullptr && bytes >= sizeof(BlobHeader), "not a packed-weight blob");
+  BlobHeader h;
+  std::memcpy(&h, blob, sizeof(h));
+  EDMP_REQUIRE(std::memcmp(h.magic, "EDMPBLOB", 8) == 0, "not a packed-weight blob (bad magic)");
+  if (h.version != kBlobLayoutVersion) {
+    set_error("unet_create_from_blob: stale blob (layout version " + std::to_string(h.version) + ", this library packs version " +
+              std::to_string(kBlobLayoutVersion) + "): repack from the state_dict");
+    return 4;
+  }
+  EDMP_REQUIRE(h.n_dims <= 8, "corrupt blob header");
+  int dims[8];
+  for (uint32_t i = 0; i < h.n_dims; ++i) dims[i] = (int)h.dims[i];
+  return unet_create_impl(nullptr, (size_t)h.n_params, dims, (int)h.n_dims, (int)h.precision, max_rows, blob, bytes, false, out);
 }
 
 int unet_precision(const UNet* u) { return u->precision; }
@@ -1333,6 +1476,7 @@ int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStrea
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
+  NvtxRange range("edmp_unet_forward");
   if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
   for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, eps, st);
   if (!u->final_fused) {

@@ -9,6 +9,13 @@ size_t unet_param_count(const int* dims, int n_dims);
 int unet_create(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
                 int max_rows, UNet** out);
 void unet_destroy(UNet* u);
+// packed-weight blob: engine from a state_dict while recording every packed device image;
+// read the blob out; engine straight from a blob (no repacking; rc 4 = stale / mismatching blob -> repack)
+int unet_pack(const float* params, size_t n_params, const int* dims, int n_dims, int precision, int max_rows, UNet** out);
+int unet_blob_layout_version();
+size_t unet_blob_bytes(const UNet* u);
+int unet_blob_read(UNet* u, void* dst, size_t cap);
+int unet_create_from_blob(const void* blob, size_t bytes, int max_rows, UNet** out);
 // eps[rows,7,50] = model(x[rows,7,50], t)
 int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st);
 int unet_read_activation(UNet* u, const char* name, int rows, float* out, int* C, int* L, cudaStream_t st);

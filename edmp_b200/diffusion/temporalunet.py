@@ -5,8 +5,10 @@ diffusion/models/temporalunet.py:9-100, but it is not an nn.Module: the paramete
 ordered dict and every forward runs in libedmp_b200.so (edmp_unet_forward).  There is no CPU path.
 """
 import ctypes
+import hashlib
 import math
 import os
+import warnings
 from collections import OrderedDict
 
 import numpy as np
@@ -80,8 +82,11 @@ def _default_init(table, generator=None):
 
 class TemporalUNet:
 
+    #: environment knobs that change which kernels / tile shapes the engine plans (and therefore the packed layouts)
+    PLAN_ENV = ("EDMP_CG2", "EDMP_NO_CG2", "EDMP_NO_NARROW", "EDMP_TC_V1", "EDMP_PM_V1", "EDMP_NO_PM")
+
     def __init__(self, model_name, input_dim, time_dim, device, dims=(32, 64, 128, 256),
-                 precision=None, max_rows=64):
+                 precision=None, max_rows=64, blob_cache=None):
         """``precision``: arithmetic mode of the contractions.  The reference's call site passes none
         (infer_serial.py:50), so the default is the benchmarked parity-grade tensor-core mode: ``f16x3`` (tcgen05,
         IEEE-half hi/lo operand split), or whatever ``EDMP_PRECISION`` names (``fp32`` = CUDA-core kernels)."""
@@ -96,6 +101,13 @@ class TemporalUNet:
         self.precision = precision
         self._max_rows = int(max_rows)
         self._handle = None
+        #: versioned on-disk cache of the packed-weight blob under <model_name>/edmp_cache.
+        #: None = on for weights that came from the checkpoint on disk (load()), off for in-memory state_dicts;
+        #: EDMP_BLOB_CACHE=0 / 1 overrides.
+        self.blob_cache = blob_cache
+        self._from_checkpoint = False
+        self._sha = None
+        self.engine_source = None      # "state_dict" | "blob" | "packed" (how the current engine was built)
         self._table = unet_key_table(self.input_dim, self.dims)
         self.training = False
         self.model_name = model_name
@@ -135,6 +147,8 @@ class TemporalUNet:
                 raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(v.shape), shape))
             new[k] = v.contiguous()
         self._sd = new
+        self._from_checkpoint = False
+        self._sha = None
         self._release()
 
     def parameters(self):
@@ -151,6 +165,7 @@ class TemporalUNet:
     def load(self):
         self.losses = np.load(self.model_name + "/losses.npy")
         self.load_state_dict(torch.load(self.model_name + "/weights_latest.pt", map_location="cpu"))
+        self._from_checkpoint = True
         print("Loaded Model at " + str(self.losses.size) + " epochs")
 
     def load_checkpoint(self, checkpoint):
@@ -174,6 +189,42 @@ class TemporalUNet:
         """All tensors flattened and concatenated in state_dict order: what edmp_unet_create takes."""
         return torch.cat([v.reshape(-1) for v in self._sd.values()]).contiguous().numpy()
 
+    # ---- packed-weight blob cache (SURVEY.md section 8 f-2) ------------------------------------------------------
+    def _cache_enabled(self):
+        env = os.environ.get("EDMP_BLOB_CACHE")
+        if env is not None:
+            return env not in ("0", "")
+        return self._from_checkpoint if self.blob_cache is None else bool(self.blob_cache)
+
+    @staticmethod
+    def plan_class(max_rows):
+        """The batch-size class the engine plans its tiles for: narrow column tiles below ~1300 rows (one class per
+        row-tile count up to 40), CTA pairs from 4096 rows on, plus the planning knobs of the environment."""
+        rts = (int(max_rows) + 127) // 128
+        env = "".join("%s=%s;" % (k, os.environ[k]) for k in TemporalUNet.PLAN_ENV if k in os.environ)
+        tag = "r%d%s" % (min(rts, 40), "p" if max_rows >= 4096 else "")
+        return tag + ("-" + hashlib.sha256(env.encode()).hexdigest()[:8] if env else "")
+
+    def blob_path(self, max_rows, version=None):
+        """<model dir>/edmp_cache/unet_<sha256(state_dict)[:16]>_<precision>_v<layout version>_<plan class>.blob"""
+        if self._sha is None:
+            self._sha = hashlib.sha256(self.flat_params().tobytes()).hexdigest()
+        if version is None:
+            version = _lib.load().edmp_unet_blob_layout_version()
+        return os.path.join(self.model_name, "edmp_cache", "unet_%s_%s_v%d_%s.blob" % (
+            self._sha[:16], self.precision, version, self.plan_class(max_rows)))
+
+    def _drop_stale_blobs(self, keep):
+        """blobs of this checkpoint / precision / plan class written by another layout version are dead weight"""
+        folder, name = os.path.split(keep)
+        head, tail = name.split("_v")[0], name.split("_v")[1].split("_", 1)[1]
+        for f in os.listdir(folder):
+            if f != name and f.startswith(head + "_v") and f.endswith("_" + tail):
+                try:
+                    os.remove(os.path.join(folder, f))
+                except OSError:
+                    pass
+
     def engine(self, rows=1):
         """Opaque edmp_unet* with a workspace for at least ``rows`` rows."""
         dev = _lib.require_cuda(self.device)
@@ -181,17 +232,47 @@ class TemporalUNet:
         if self._handle is None or rows > self._max_rows:
             self._release()
             self._max_rows = max(self._max_rows, int(rows))
-            flat = self.flat_params()
             dims = (ctypes.c_int * len(self.dims))(*self.dims)
-            expect = lib.edmp_unet_param_count(dims, len(self.dims))
-            if expect != flat.size:
-                raise _lib.EdmpError("state_dict has %d floats, library expects %d" % (flat.size, expect))
             handle = ctypes.c_void_p()
+            path = self.blob_path(self._max_rows) if self._cache_enabled() else None
             with torch.cuda.device(dev):
-                _lib.check(lib.edmp_unet_create(flat.ctypes.data_as(ctypes.c_void_p), flat.size, dims,
-                                                len(self.dims), _lib.PRECISIONS[self.precision],
-                                                self._max_rows, ctypes.byref(handle)), "edmp_unet_create")
-            self._handle = handle
+                if path is not None and os.path.exists(path):
+                    blob = np.fromfile(path, dtype=np.uint8)
+                    rc = lib.edmp_unet_create_from_blob(blob.ctypes.data_as(ctypes.c_void_p), blob.size, self._max_rows,
+                                                        ctypes.byref(handle))
+                    if rc == 0:
+                        self._handle, self.engine_source = handle, "blob"
+                        return self._handle
+                    warnings.warn("edmp_b200: dropping the cached packed-weight blob %s (%s)" % (
+                        path, lib.edmp_last_error().decode()), RuntimeWarning)
+                    try:
+                        os.remove(path)
+                    except OSError:
+                        pass
+                    handle = ctypes.c_void_p()
+                flat = self.flat_params()
+                expect = lib.edmp_unet_param_count(dims, len(self.dims))
+                if expect != flat.size:
+                    raise _lib.EdmpError("state_dict has %d floats, library expects %d" % (flat.size, expect))
+                create = lib.edmp_unet_pack if path is not None else lib.edmp_unet_create
+                _lib.check(create(flat.ctypes.data_as(ctypes.c_void_p), flat.size, dims, len(self.dims),
+                                  _lib.PRECISIONS[self.precision], self._max_rows, ctypes.byref(handle)),
+                           "edmp_unet_pack" if path is not None else "edmp_unet_create")
+                self._handle, self.engine_source = handle, "state_dict"
+                if path is not None:
+                    try:
+                        n = lib.edmp_unet_blob_bytes(handle)
+                        blob = np.empty(n, dtype=np.uint8)
+                        _lib.check(lib.edmp_unet_blob_read(handle, blob.ctypes.data_as(ctypes.c_void_p), n),
+                                   "edmp_unet_blob_read")
+                        os.makedirs(os.path.dirname(path), exist_ok=True)
+                        tmp = path + ".tmp%d" % os.getpid()
+                        blob.tofile(tmp)
+                        os.replace(tmp, path)            # atomic: a concurrent reader sees the old file or the new one
+                        self._drop_stale_blobs(path)
+                        self.engine_source = "packed"
+                    except OSError as e:                 # read-only model directory: run without the cache
+                        warnings.warn("edmp_b200: cannot write the packed-weight cache (%s)" % e, RuntimeWarning)
         return self._handle
 
     def forward(self, x, t):

@@ -65,6 +65,21 @@ size_t edmp_unet_param_count(const int* dims, int n_dims);
 int edmp_unet_create(const float* params_h, size_t n_params, const int* dims, int n_dims,
                      int precision, int max_rows, edmp_unet** out);
 void edmp_unet_destroy(edmp_unet* u);
+/* ---- packed-weight blob (the checkpoint side is temporalunet.py:78-92 save / load) -------
+ * edmp_unet_pack = edmp_unet_create that also RECORDS every device image it uploads (repacked hi / lo weight tiles in
+ * their UMMA layouts, per-channel vectors, the 255-row time-embedding table) as one host blob; edmp_unet_blob_bytes /
+ * edmp_unet_blob_read hand it out (the read releases the engine's host copy); edmp_unet_create_from_blob builds an
+ * engine from such a blob with no state_dict and no repacking.  The blob carries the layout version
+ * (edmp_unet_blob_layout_version), the precision, dims, and per item the tile geometry it was packed for: a stale or
+ * mismatching blob (other layout version, other batch-size class / kernel generation) is refused with rc 4 and the
+ * caller repacks from the state_dict.  The host class keeps the blobs as a versioned on-disk cache next to the
+ * checkpoint (edmp_b200/diffusion/temporalunet.py). */
+int edmp_unet_pack(const float* params_h, size_t n_params, const int* dims, int n_dims, int precision, int max_rows,
+                   edmp_unet** out);
+size_t edmp_unet_blob_bytes(const edmp_unet* u);
+int edmp_unet_blob_read(edmp_unet* u, void* dst_h, size_t capacity);
+int edmp_unet_create_from_blob(const void* blob_h, size_t nbytes, int max_rows, edmp_unet** out);
+int edmp_unet_blob_layout_version(void);
 /* eps[rows,7,50] = model(x[rows,7,50], t), t in 1..255 (one t for the whole batch,
  * diffusion.py:320).  x_d/eps_d float32 device pointers. */
 int edmp_unet_forward(edmp_unet* u, const float* x_d, int t, int rows, float* eps_d, void* stream);
