@@ -57,6 +57,15 @@ class FakeLib:
         self._handle(out)
         return 0
 
+    # (the checkpoint comes from disk, so the host class packs and caches the weight blob: edmp_unet_pack + blob read)
+    do_edmp_unet_pack = do_edmp_unet_create
+
+    def do_edmp_unet_blob_bytes(self, unet):
+        return 64
+
+    def do_edmp_unet_blob_layout_version(self):
+        return 1
+
     def do_edmp_sampler_create(self, T, thresh, rows, out):
         self._handle(out)
         return 0
@@ -178,7 +187,8 @@ general:
     total = 3 * 2
     # :50 TemporalUNet(model_name=, input_dim=, time_dim=32, dims=, device=): the engine is built once, with the whole
     # checkpoint, in the shipped default precision (the reference passes none) = the benchmarked f16x3 mode
-    (params, n_params, dims, n_dims, precision, max_rows, _), = by["edmp_unet_create"]
+    (params, n_params, dims, n_dims, precision, max_rows, _), = by["edmp_unet_pack"]
+    assert len(os.listdir(os.path.join(model_dir, "TemporalUNetModel255_N50", "edmp_cache"))) == 1
     assert n_params == 29938471 and [dims[i] for i in range(n_dims)] == [32, 64, 128, 256, 512, 512]
     assert precision == _lib.PRECISIONS["f16x3"] and max_rows >= total
     # :112 IntersectionVolumeGuide(obstacle_config=, device=, guide_cfgs=, batch_size=): one scene per problem
