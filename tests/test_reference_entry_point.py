@@ -201,9 +201,16 @@ general:
         assert (a[6], a[7]) == (total, total)
     # :134-143 denoise_guided(model=, guide=, batch_size=, traj_len=, num_channels=, condition=True, benchmarking=True,
     #                         start=, goal=, guidance_schedule=): all 255 steps in one call, recorded numpy noise tape
-    assert len(by["edmp_sample_guided"]) == 2
-    for a in by["edmp_sample_guided"]:
-        assert (a[8], a[9], a[10]) == (total, 255, 0) and a[6] is not None and a[11] is not None
+    #   (the numpy noise stream reaches the device in 16-step chunks: 16 calls per problem, contiguous in t)
+    calls = by["edmp_sample_guided"]
+    assert len(calls) == 2 * 16
+    for prob in (calls[:16], calls[16:]):
+        t = 255
+        for a in prob:
+            assert a[8] == total and a[9] == t and a[6] is not None          # rows, t_start, the noise chunk
+            assert (a[11] is not None) == (a[10] == 0)                       # final costs with the last chunk only
+            t = a[10]
+        assert t == 0
     assert all(a[1] == 1 for a in by["edmp_sampler_set_condition"])
     # :147 choose_best_trajectory(start_joints, goal_joints, trajectories): argmin of the device-side final costs
     assert len(by["edmp_guide_final_cost"]) == 2 and all(a[4] == total for a in by["edmp_guide_final_cost"])
