@@ -88,6 +88,29 @@ struct Tc2Args {
   unsigned* range_flag;           // set when a stored IEEE-half hi part is infinite (conv_tc.cuh range_track), may be null
 };
 
+// One persistent launch = a RUN of consecutive layers.  Every role (operand producer, MMA issue,
+// epilogue) walks the layers of the run in order and keeps its ring / accumulator state across layer boundaries, so a
+// CTA's last epilogue of layer i runs under its first mainloop of layer i+1, the weight and activation stages never
+// drain between layers, and barrier set-up / TMEM allocation happen once per run.  Layers of a run share ONE
+// shared-memory carve-up (the most demanding layer decides), the cta_group, the zero-slot layout and the number of
+// issuing warps; single-buffered layers (1x1-residual phases: 512 accumulator columns) take both TMEM buffers under
+// a both-buffers handshake.  Row tiles are handed from layer to layer through the global `done` / `dep` counters as
+// between launches.  Work assignment: the tiles of all layers of a run form one round-robin sequence over the
+// walkers (rot[j] = tiles of layers 0..j-1 mod walkers), so that the odd tiles of non-divisible layers spread evenly.
+constexpr int kT2MaxRun = 14;
+// (NR = capacity: single-layer launches use Tc2RunT<1> -- a 0.5 KB kernel parameter instead of 7 KB)
+template <int NR>
+struct Tc2RunT {
+  int n;                                   // layers
+  int a_stages, b_stages;                  // operand stage rings of the run
+  int b_stage_stride, b_lo_off, b_real_off, b_total_bytes;   // weight stage geometry (bytes)
+  int b_pad, slot_bytes;                   // zero tap slots ([Z][real][Z]... layout) of slot_bytes each
+  int mma_warps, split;
+  int rot[NR];
+  Tc2Args l[NR];
+};
+typedef Tc2RunT<kT2MaxRun> Tc2Run;
+
 namespace t2 {
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -192,8 +215,8 @@ __device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 5, %0;" ::"n"(kT2EpiThreads) : "memory"); }
 }  // namespace t2
 
-template <int EL, int CG>
-__global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args a) {
+template <int EL, int CG, int NR>
+__global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_constant__ Tc2RunT<NR> r) {
   static_assert(EL != TC_EL_TF32, "conv_tc2 uses 16-bit operand elements");
   using E = TcElem<EL>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -208,39 +231,35 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? t2::cluster_ctarank() : 0u;
-  const uint32_t nsplit = CG == 1 ? (uint32_t)a.nsplit : 1u;               // column split of a GroupNorm group over a cluster
+  const uint32_t nsplit = CG == 1 ? (uint32_t)r.l[0].nsplit : 1u;          // column split of a GroupNorm group over a cluster (single-layer launches)
   const uint32_t crank = nsplit > 1 ? t2::cluster_ctarank() : 0u;
-  const int nparts = a.split ? 2 : 1;
+  const int nparts = r.split ? 2 : 1;
   const int a_stage_bytes = kTcBlockBytes * nparts;
-  int max_slots = a.ph[0].slots;
-  if (a.n_phases > 1 && a.ph[1].slots > max_slots) max_slots = a.ph[1].slots;
-  const int ctl = a.ct / CG;                                // weight rows per slot staged by this CTA
-  const int b_part_bytes = max_slots * ctl * 128;
-  const int b_stage_bytes = b_part_bytes * nparts;
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + a.a_stages * a_stage_bytes;
-  // Weight stages.  Plain: [stage][hi | lo][max_slots x ctl rows].  Padded (full-window CTA-pair layers whose first
+  uint8_t* b_smem = smem + r.a_stages * a_stage_bytes;
+  // Weight stages.  Plain: [stage][hi | lo][slots x rows].  Padded (full-window CTA-pair layers whose first
   // and last tap slot are all zero): per part [Z][real slots of stage 0][Z][real slots of stage 1][Z]... -- the zero
   // slots are written once, never copied, and shared by neighbouring stages; a stage's window view starts at its
-  // leading zero slot.
-  const int slot_bytes = ctl * 128;
-  const int b_stage_stride = a.b_pad ? (max_slots + 1) * slot_bytes : b_stage_bytes;
-  const int b_lo_off = a.b_pad ? (a.b_stages * (max_slots + 1) + 1) * slot_bytes : b_part_bytes;
-  const int b_real_off = a.b_pad ? slot_bytes : 0;
-  const int b_total_bytes = a.b_pad ? nparts * b_lo_off : a.b_stages * b_stage_bytes;
-  float* s_part = reinterpret_cast<float*>(b_smem + b_total_bytes);   // GroupNorm pieces [piece][mean | M2][128 rows]
-  const int n_tiles = (a.n_row_tiles / CG) * a.n_col_tiles;
+  // leading zero slot.  The geometry is the run's (Tc2Run), not a layer's.
+  const int b_stage_stride = r.b_stage_stride, b_lo_off = r.b_lo_off, b_real_off = r.b_real_off;
+  float* s_part = reinterpret_cast<float*>(b_smem + r.b_total_bytes);   // GroupNorm pieces [piece][mean | M2][128 rows]
   const int unit0 = blockIdx.x / CG, n_walkers = gridDim.x / CG;
+  // this walker's first tile of layer li, and that layer's tile count
+  // (NR == 1: the layer index is the constant 0, so that every a.<field> below is a fixed constant-bank operand as in a
+  // single-layer kernel; NR > 1 pays an indexed constant load per access)
+  auto LX = [](int li) { return NR == 1 ? 0 : li; };
+  auto first_tile = [&](int li) { if (NR == 1) return unit0; const int t = unit0 - r.rot[li]; return t < 0 ? t + n_walkers : t; };
+  auto layer_tiles = [&](int li) { return (r.l[LX(li)].n_row_tiles / CG) * r.l[LX(li)].n_col_tiles; };
 
-  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  long long* dbg = r.l[0].dbg ? r.l[0].dbg + (size_t)blockIdx.x * 16 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); umma::mbar_init(pa_full + i, 1); }
+    for (int i = 0; i < r.a_stages; ++i) { umma::mbar_init(a_full + i, 1); umma::mbar_init(a_empty + i, 1); umma::mbar_init(pa_full + i, 1); }
     // (with two issuing warps each commits the weight stage / the accumulator after its own last step)
-    for (int i = 0; i < a.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, a.mma_warps); umma::mbar_init(pb_full + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, a.mma_warps); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
+    for (int i = 0; i < r.b_stages; ++i) { umma::mbar_init(b_full + i, 1); umma::mbar_init(b_empty + i, r.mma_warps); umma::mbar_init(pb_full + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(acc_full + i, r.mma_warps); umma::mbar_init(acc_empty + i, kT2EpiWarps * CG); }
     for (int i = 0; i < 2; ++i) umma::mbar_init(xg_full + i, nsplit > 1 ? (nsplit - 1) * 4 : 1);   // one arrive per peer and lane quarter
     umma::fence_barrier_init();
   }
@@ -252,9 +271,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       umma::tmem_alloc<512>(&tmem_slot);
     }
   }
-  if (a.b_pad) {
+  if (r.b_pad) {
     // zero slots: one before every stage's real slots and one after the last stage, in both parts
-    const int nz = a.b_stages + 1, words = slot_bytes >> 4;
+    const int nz = r.b_stages + 1, words = r.slot_bytes >> 4;
     for (int i = threadIdx.x; i < nparts * nz * words; i += blockDim.x) {
       const int w = i % words, z = (i / words) % nz, part_i = i / (words * nz);
       reinterpret_cast<uint4*>(b_smem + part_i * b_lo_off + z * b_stage_stride)[w] = make_uint4(0, 0, 0, 0);
@@ -268,43 +287,47 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   const uint32_t tmem_base = tmem_slot;
   // everything above overlapped the previous kernel; activations are read below.  Chained layers synchronise per row
   // tile instead (the producer thread, before a tile's first activation load)
-  if (a.dep == nullptr) pdl_wait();
+  if (r.l[0].dep == nullptr) pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== operand producer: ONE thread polls the "stage empty" barriers of both streams (activations, weights)
-    // without blocking and issues bulk copies of ready-made operand blocks; both streams run ahead across tile
-    // boundaries as far as the stages allow =====
+    // without blocking and issues bulk copies of ready-made operand blocks; both streams run ahead across tile AND
+    // layer boundaries as far as the stages allow =====
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      int ta = unit0, pa = 0, cca = 0, lia = 0;     // activation stream position (tile, phase, chunk, input position)
-      int tb = unit0, pb = 0, ccb = 0;              // weight stream position
-      int ta_ready = -1;                            // tile whose row-tile dependency has been observed
+      // stream positions: (layer, tile, phase, chunk, input position) of the activations, (layer, tile, phase, chunk) of the weights
+      int la = 0, ta = first_tile(0), nta = layer_tiles(0), pa = 0, cca = 0, lia = 0;
+      int lb = 0, tb = first_tile(0), ntb = layer_tiles(0), pb = 0, ccb = 0;
+      while (la < r.n && ta >= nta) { if (++la < r.n) { ta = first_tile(la); nta = layer_tiles(la); } }   // layers without a tile for this walker
+      while (lb < r.n && tb >= ntb) { if (++lb < r.n) { tb = first_tile(lb); ntb = layer_tiles(lb); } }
+      if (la < r.n) while (r.l[LX(la)].ph[0].sched[lia].n_slots == 0) ++lia;                                    // leading unused positions
+      int ta_ready = -1;                            // (layer, tile) whose row-tile dependency has been observed
       long long dep_t0 = 0;
-      // skip leading unused positions
-      while (ta < n_tiles && a.ph[pa].sched[lia].n_slots == 0) ++lia;
-      while (ta < n_tiles || tb < n_tiles) {
-        bool a_go = ta < n_tiles && t2::test(a_empty + as, aph ^ 1);
-        if (a_go && a.dep != nullptr && ta != ta_ready) {
+      while (la < r.n || lb < r.n) {
+        bool a_go = la < r.n && t2::test(a_empty + as, aph ^ 1);
+        if (a_go && r.l[LX(la)].dep != nullptr && ((la << 20) | ta) != ta_ready) {
           // first activation load of this tile: the producing layer must have finished this row tile (the weight
           // stream below keeps being served meanwhile)
+          const Tc2Args& a = r.l[LX(la)];
           const int rt_dep = (ta >> a.nct_log2) * CG + (int)rank;
           // (a pair's padding row tile past the batch has no producer: its operand blocks are the zero-filled tail)
           if (rt_dep * kTcRows < a.rows && t2::ld_acquire(a.dep + rt_dep) < a.dep_target) {
             a_go = false;
             if (dep_t0 == 0) dep_t0 = clock64();
             else if (clock64() - dep_t0 > (1ll << 32)) {   // ~2 s: a protocol bug traps instead of hanging the GPU
-              printf("edmp: conv_tc2 row-tile dependency timed out (block %d, row tile %d: %d of %d)\n", blockIdx.x, rt_dep,
-                     t2::ld_acquire(a.dep + rt_dep), a.dep_target);
+              printf("edmp: conv_tc2 row-tile dependency timed out (block %d, layer %d of the run, row tile %d: %d of %d)\n",
+                     blockIdx.x, la, rt_dep, t2::ld_acquire(a.dep + rt_dep), a.dep_target);
               __trap();
             }
           } else {
             dep_t0 = 0;
             asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (bulk copy) reads
-            ta_ready = ta;
+            ta_ready = (la << 20) | ta;
           }
         }
         if (a_go) {
+          const Tc2Args& a = r.l[LX(la)];
           const Tc2Phase& ph = a.ph[pa];
           const int ka = ph.a.C >> E::kShift, kb = ph.b.C >> E::kShift;
           const bool first = cca < ka;
@@ -316,59 +339,75 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
           uint8_t* dst = a_smem + as * a_stage_bytes;
           umma::bulk_g2s(dst, (const uint8_t*)op.hi + blk, kTcBlockBytes, a_full + as);
-          if (a.split) umma::bulk_g2s(dst + kTcBlockBytes, (const uint8_t*)op.lo + blk, kTcBlockBytes, a_full + as);
-          if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
-          // advance (tile, phase, chunk, position), skipping unused positions
-          do {
-            if (++lia == ph.lin) {
+          if (r.split) umma::bulk_g2s(dst + kTcBlockBytes, (const uint8_t*)op.lo + blk, kTcBlockBytes, a_full + as);
+          if (++as == (uint32_t)r.a_stages) { as = 0; aph ^= 1; }
+          // advance (layer, tile, phase, chunk, position), skipping unused positions and layers without a tile
+          for (;;) {
+            const Tc2Args& c = r.l[LX(la)];
+            const Tc2Phase& cp = c.ph[pa];
+            if (++lia == cp.lin) {
               lia = 0;
-              if (++cca == ka + kb) {
+              if (++cca == ((cp.a.C + cp.b.C) >> E::kShift)) {
                 cca = 0;
-                if (++pa == a.n_phases) { pa = 0; ta += n_walkers; }
+                if (++pa == c.n_phases) {
+                  pa = 0;
+                  ta += n_walkers;
+                  while (la < r.n && ta >= nta) { if (++la < r.n) { ta = first_tile(la); nta = layer_tiles(la); } }
+                }
               }
             }
-          } while (ta < n_tiles && a.ph[pa].sched[lia].n_slots == 0);
+            if (la >= r.n || r.l[LX(la)].ph[pa].sched[lia].n_slots != 0) break;
+          }
         }
-        if (tb < n_tiles && t2::test(b_empty + bs, bph ^ 1)) {
+        if (lb < r.n && t2::test(b_empty + bs, bph ^ 1)) {
+          const Tc2Args& a = r.l[LX(lb)];
           const Tc2Phase& ph = a.ph[pb];
           const int kc = (ph.a.C + ph.b.C) >> E::kShift;
           const int nt = tb & (a.n_col_tiles - 1);
-          const uint32_t wtile_bytes = (uint32_t)(ph.slots * ctl * 128);
+          const uint32_t wtile_bytes = (uint32_t)(ph.slots * (a.ct / CG) * 128);
           const size_t woff = (((size_t)nt * kc + ccb) * CG + rank) * wtile_bytes;
           umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes * (uint32_t)nparts);
           uint8_t* dst = b_smem + bs * b_stage_stride + b_real_off;
           umma::bulk_g2s(dst, (const uint8_t*)ph.w_hi + woff, wtile_bytes, b_full + bs);
-          if (a.split) umma::bulk_g2s(dst + b_lo_off, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
-          if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
+          if (r.split) umma::bulk_g2s(dst + b_lo_off, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
+          if (++bs == (uint32_t)r.b_stages) { bs = 0; bph ^= 1; }
           if (++ccb == kc) {
             ccb = 0;
-            if (++pb == a.n_phases) { pb = 0; tb += n_walkers; }
+            if (++pb == a.n_phases) {
+              pb = 0;
+              tb += n_walkers;
+              while (lb < r.n && tb >= ntb) { if (++lb < r.n) { tb = first_tile(lb); ntb = layer_tiles(lb); } }
+            }
           }
         }
       }
     }
   } else if (warp == 1 || warp == 2) {
     uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-    const int mw = warp - 1, nw = a.mma_warps;   // issuing warp index, number of issuing warps
+    const int mw = warp - 1, nw = r.mma_warps;   // issuing warp index, number of issuing warps
     if (CG == 2 && rank == 1) {
       // ===== peer of a CTA pair: relay "my stage is full" to the leader, which issues the MMAs for both =====
       if (mw == 0)
-      for (int t = unit0; t < n_tiles; t += n_walkers) {
-        for (int p = 0; p < a.n_phases; ++p) {
-          const Tc2Phase& ph = a.ph[p];
-          const int kc = (ph.a.C + ph.b.C) >> E::kShift;
-          for (int cc = 0; cc < kc; ++cc) {
-            t2::wait(b_full + bs, bph);
-            if (lane == 0) t2::mbar_arrive_remote(pb_full + bs, 0);
-            __syncwarp();
-            for (int li = 0; li < ph.lin; ++li) {
-              if (ph.sched[li].n_slots == 0) continue;
-              t2::wait(a_full + as, aph);
-              if (lane == 0) t2::mbar_arrive_remote(pa_full + as, 0);
+      for (int li = 0; li < r.n; ++li) {
+        const Tc2Args& a = r.l[LX(li)];
+        const int n_tiles = layer_tiles(li);
+        for (int t = first_tile(li); t < n_tiles; t += n_walkers) {
+          for (int p = 0; p < a.n_phases; ++p) {
+            const Tc2Phase& ph = a.ph[p];
+            const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+            for (int cc = 0; cc < kc; ++cc) {
+              t2::wait(b_full + bs, bph);
+              if (lane == 0) t2::mbar_arrive_remote(pb_full + bs, 0);
               __syncwarp();
-              if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+              for (int li2 = 0; li2 < ph.lin; ++li2) {
+                if (ph.sched[li2].n_slots == 0) continue;
+                t2::wait(a_full + as, aph);
+                if (lane == 0) t2::mbar_arrive_remote(pa_full + as, 0);
+                __syncwarp();
+                if (++as == (uint32_t)r.a_stages) { as = 0; aph ^= 1; }
+              }
+              if (++bs == (uint32_t)r.b_stages) { bs = 0; bph ^= 1; }
             }
-            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
           }
         }
       }
@@ -381,21 +420,39 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
       const uint64_t desc0 = umma::make_desc_sw128(0);     // weight tiles: SWIZZLE_128B rows
       const uint64_t desc_a0 = tc_act_desc0();             // activation blocks: chunk-major, no swizzle (conv_tc.cuh)
-      uint32_t buf = 0, eph = 0;   // accumulator buffer and the parity of its "empty" barrier
+      // accumulator buffers: `buf` = next buffer of a double-buffered tile; ne[b] = how often acc_empty[b] has been waited
+      // for.  A single-buffered tile (512 columns) waits for BOTH buffers and leaves buf = 0 (the epilogue mirrors this).
+      uint32_t buf = 0, ne0 = 0, ne1 = 0;
       uint32_t step = 0;
       long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0;
       if (nw == 2 && mw == 1) t2::token_pass(0);   // the first token
-      for (int t = unit0; t < n_tiles; t += n_walkers) {
+      for (int li = 0; li < r.n; ++li) {
+      const Tc2Args& a = r.l[LX(li)];
+      const int n_tiles = layer_tiles(li);
+      const int ctl = a.ct / CG;                   // weight rows per slot staged by this CTA
+      for (int t = first_tile(li); t < n_tiles; t += n_walkers) {
+        uint32_t ab;                               // accumulator buffer of this tile
         {
           const long long tw = dbg ? clock64() : 0;
-          t2::wait(acc_empty + buf, eph ^ 1);
+          if (a.acc_bufs == 2) {
+            ab = buf;
+            t2::wait(acc_empty + ab, ((ab ? ne1 : ne0) & 1u) ^ 1u);
+            if (ab) ++ne1; else ++ne0;
+            buf ^= 1;
+          } else {
+            t2::wait(acc_empty + 0, (ne0 & 1u) ^ 1u);
+            t2::wait(acc_empty + 1, (ne1 & 1u) ^ 1u);
+            ++ne0; ++ne1;
+            ab = 0; buf = 0;
+          }
           if (dbg) w_acc += clock64() - tw;
         }
         umma::tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * (uint32_t)a.acc_stride;
+        const uint32_t acc0 = tmem_base + ab * (uint32_t)a.acc_stride;
         for (int p = 0; p < a.n_phases; ++p) {
           const Tc2Phase& ph = a.ph[p];
           const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+          const int ph_lin = ph.lin, ph_dcol = ph.d_col, ph_cstep = ph.col_step, l_ct = a.ct;   // (registers: the issuing warps have plenty)
           for (int cc = 0; cc < kc; ++cc) {
             {
               const long long tw = dbg ? clock64() : 0;
@@ -405,8 +462,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
             }
             const uint32_t b_base = b0 + bs * (uint32_t)b_stage_stride;
             const bool last_chunk = (p == a.n_phases - 1) && (cc == kc - 1);
-            for (int li = 0; li < ph.lin; ++li, ++step) {
-              const Tc2Sched s = ph.sched[li];
+            for (int li2 = 0; li2 < ph_lin; ++li2, ++step) {
+              const Tc2Sched s = ph.sched[li2];
               if (s.n_slots == 0) continue;   // (never with two issuing warps, the host checks)
               const bool mine = nw == 1 || (int)(step & 1) == mw;
               if (mine) {
@@ -422,15 +479,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                 // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are
                 // written for the first time -> two runs with their own accumulate flag; afterwards one run
                 const int n_first = (cc == 0) ? s.n_acc : s.n_slots;
-                const bool my_last_in_chunk = nw == 1 ? (li == ph.lin - 1) : (li >= ph.lin - 2);
+                const bool my_last_in_chunk = nw == 1 ? (li2 == ph_lin - 1) : (li2 >= ph_lin - 2);
                 if (nw == 2) { t2::token_wait(mw); umma::tc_fence_after(); }
 #pragma unroll 1
                 for (int run = 0; run < 2; ++run) {
                   const int sl0 = run == 0 ? 0 : n_first;
                   const int n = run == 0 ? n_first : s.n_slots - n_first;
                   if (n <= 0) continue;
-                  const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows * CG, n * a.ct);
-                  const uint32_t d = acc0 + (uint32_t)(ph.d_col + (s.lo_begin + sl0) * ph.col_step);
+                  const uint32_t idesc = umma::make_idesc(E::kFmt, kTcRows * CG, n * l_ct);
+                  const uint32_t d = acc0 + (uint32_t)(ph_dcol + (s.lo_begin + sl0) * ph_cstep);
                   const uint32_t b_off = b_base + (uint32_t)((s.slot_begin + sl0) * ctl * 128);
                   const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
                   const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_lo_off) & 0x3FFFF) >> 4);
@@ -440,7 +497,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                     for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
                       const uint32_t acc = accf | (uint32_t)(ks > 0);
                       if (CG == 2) {
-                        if (a.split) {
+                        if (r.split) {
                           t2::mma_f16_cg2(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                           t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
                           t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
@@ -448,7 +505,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                           t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                         }
                       } else {
-                        if (a.split) {
+                        if (r.split) {
                           umma::mma_bf16(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
                           umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
                           umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
@@ -465,17 +522,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                   // step of the chunk / the tile also the weight stage / the accumulator
                   if (CG == 2) t2::commit_cg2(a_empty + as); else umma::mma_commit(a_empty + as);
                   if (my_last_in_chunk) { if (CG == 2) t2::commit_cg2(b_empty + bs); else umma::mma_commit(b_empty + bs); }
-                  if (my_last_in_chunk && last_chunk) { if (CG == 2) t2::commit_cg2(acc_full + buf); else umma::mma_commit(acc_full + buf); }
+                  if (my_last_in_chunk && last_chunk) { if (CG == 2) t2::commit_cg2(acc_full + ab); else umma::mma_commit(acc_full + ab); }
                 }
                 __syncwarp();
                 if (nw == 2) { umma::tc_fence_before(); t2::token_pass(mw ^ 1); }
               }
-              if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+              if (++as == (uint32_t)r.a_stages) { as = 0; aph ^= 1; }
             }
-            if (++bs == (uint32_t)a.b_stages) { bs = 0; bph ^= 1; }
+            if (++bs == (uint32_t)r.b_stages) { bs = 0; bph ^= 1; }
           }
         }
-        if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) eph ^= 1; } else { eph ^= 1; }
+      }
       }
       if (nw == 2 && (int)(step & 1) == mw) t2::token_wait(mw);   // consume the last token
       if (dbg && lane == 0 && mw == 0) { dbg[2] = w_acc; dbg[3] = w_b; dbg[4] = w_a; dbg[5] = clock64() - t_begin; }
@@ -487,6 +544,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     const int et = threadIdx.x - kT2EpiWarp0 * 32;
     const int row_local = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
+    uint32_t xg_par = 0, xg_ph = 0;
+    uint32_t hmax = 0;                                    // largest |hi| half pattern stored (operand range check)
+    // accumulator buffers, mirroring the MMA warps: `buf` = next buffer of a double-buffered tile, nf[b] = how often
+    // acc_full[b] has been waited for; a single-buffered tile uses buffer 0's barrier and releases BOTH buffers
+    uint32_t buf = 0, nf0 = 0, nf1 = 0;
+    long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
+    int tile_par = 0;
+    for (int li = 0; li < r.n; ++li) {
+    const Tc2Args& a = r.l[LX(li)];
+    const int n_tiles = layer_tiles(li);
     const int L = a.lout, ct = a.ct, cg = a.cg;
     const int n_units = (L * ct) >> 4;
     const bool two = cg == 8;                             // a 16-column unit spans two GroupNorm groups
@@ -495,19 +563,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
     const int kch_out = a.cout >> E::kShift;
     const int half_cols = (L * ct) >> 1;                  // half_layout: columns of one half
     const int ct_log2 = a.ct_log2, cg_log2 = a.cg_log2;
-    float* my_part = s_part + row_local;   // [piece][mean | M2][128 rows]
     const int n_pieces_alloc = n_units * (two ? 2 : 1);
     float* my_stat = my_part + n_pieces_alloc * 256;   // [group][mean | rstd][128 rows]
     const int gw = min(cg, ct);                           // channels of a group inside this column tile (ct < cg: column split)
     const int n_groups = two ? (ct >> 3) : max(1, ct >> cg_log2);
     const float inv_pieces = 1.0f / (float)(L * (two ? 1 : (gw >> 4)));
     float* s_xg = my_part + (n_pieces_alloc + n_groups) * 256;   // nsplit > 1: [tile parity][source rank][mean | M2][128 rows]
-    uint32_t xg_par = 0, xg_ph = 0;
-    uint32_t hmax = 0;                                    // largest |hi| half pattern stored (operand range check)
-    uint32_t buf = 0, fph = 0;
-    long long w_full = 0, t_busy = 0, t_stats = 0, t_bar = 0, t_fin = 0, t_par = 0;
-    int tile_par = 0;
-    for (int t = unit0; t < n_tiles; t += n_walkers) {
+    for (int t = first_tile(li); t < n_tiles; t += n_walkers) {
       const int nt = t & (a.n_col_tiles - 1);
       const int rt = (t >> a.nct_log2) * CG + (int)rank;
       const int grow = rt * kTcRows + row_local;
@@ -525,15 +587,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       }
       t2::bar_epilogue();   // also: every thread is past the previous tile's reads of the GroupNorm pieces
       if (dbg) t_par += clock64() - tp0;
+      uint32_t ab;                               // accumulator buffer of this tile
       {
         const long long tw = dbg ? clock64() : 0;
-        t2::wait(acc_full + buf, fph);
+        if (a.acc_bufs == 2) { ab = buf; buf ^= 1; } else { ab = 0; buf = 0; }
+        t2::wait(acc_full + ab, (ab ? nf1 : nf0) & 1u);
+        if (ab) ++nf1; else ++nf0;
         if (dbg) w_full += clock64() - tw;
       }
       const long long t_start = dbg ? clock64() : 0;
       __syncwarp();
       umma::tc_fence_after();
-      const uint32_t t_acc = t_lane + buf * (uint32_t)a.acc_stride;
+      const uint32_t t_acc = t_lane + ab * (uint32_t)a.acc_stride;
 
       // ---- my units: unit u = part + 4k covers accumulator columns [16u, 16u+16); two units per batch ----
       // (position, first channel within the tile) of the unit at accumulator column `col`
@@ -814,7 +879,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         // every accumulator read of this tile is complete: hand the TMEM buffer back to the MMA warp
         umma::tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + buf, 0); else umma::mbar_arrive(acc_empty + buf); }
+        if (lane == 0) {
+          if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + ab, 0); else umma::mbar_arrive(acc_empty + ab);
+          if (a.acc_bufs != 2) {   // a single-buffered tile held both buffers
+            if (CG == 2 && rank == 1) t2::mbar_arrive_remote(acc_empty + 1, 0); else umma::mbar_arrive(acc_empty + 1);
+          }
+        }
       }
       if (a.done != nullptr) {
         // publish the tile: the barrier orders every epilogue thread's stores before thread 0's GPU-scope fence (fences
@@ -824,10 +894,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         if (et == 0) { __threadfence(); atomicAdd(a.done + rt, 1); }
       }
       if (dbg) { const long long te = clock64(); t_busy += te - t_start; t_fin += te - tf0; }
-      if (a.acc_bufs == 2) { buf ^= 1; if (buf == 0) fph ^= 1; } else { fph ^= 1; }
+    }
     }
     if (dbg && et == 0) { dbg[6] = w_full; dbg[8] = t_busy; dbg[9] = t_stats; dbg[10] = t_bar; dbg[11] = t_fin; dbg[12] = t_par; }
-    range_report<EL>(hmax, a.range_flag);
+    range_report<EL>(hmax, r.l[0].range_flag);
     umma::tc_fence_before();
   }
   __syncthreads();

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <map>
 #include <string>
@@ -208,6 +209,8 @@ struct Layer {
   int cta_group = 1;            // LAYER_TC2: 2 = CTA pairs (cta_group::2)
   int b_pad = 0;                // LAYER_TC2 pairs: weight stages with shared resident zero slots
   int nsplit = 1;               // LAYER_TC2: CTAs of a cluster that share one GroupNorm group (column split, small batches)
+  int t2_max_slots = 0;         // LAYER_TC2: weight slots per stage, bytes per slot, bytes of the GroupNorm piece area
+  size_t t2_slot_bytes = 0, t2_part_bytes = 0;
   size_t tc_smem = 0;
   Act pack_src, pack_dst;       // LAYER_PACK
   int temb_off = -1;  // offset into the per-t time-embedding row, -1 = none
@@ -255,6 +258,16 @@ struct UNet {
   bool play_bad = false;
   int max_rows = 0;
   int n_launches = 0;
+  // launch units of one forward: a single layer, or a RUN of consecutive conv_tc2 layers in one persistent launch
+  struct Launch {
+    int first = 0, n = 1;         // layers [first, first + n)
+    bool run = false;             // conv_tc2 run (Tc2Run geometry below)
+    int a_stages = 0, b_stages = 0, b_stage_stride = 0, b_lo_off = 0, b_real_off = 0, b_total_bytes = 0, slot_bytes = 0;
+    size_t smem = 0;
+    std::string name;
+    double macs_per_row = 0.0;
+  };
+  std::vector<Launch> launches;
   std::vector<void*> dev_allocs;
   std::vector<Layer> layers;
   std::map<std::string, Act> acts;
@@ -678,6 +691,7 @@ struct Builder {
     ok = ok && v.a_stages >= 2;
     ly.kind = LAYER_TC2;
     ly.tc_smem = 1024 + v.a_stages * a_stage + b_bytes(v.b_stages) + part_bytes;
+    ly.t2_max_slots = max_slots; ly.t2_slot_bytes = slot_bytes; ly.t2_part_bytes = part_bytes;
   }
 
   static TcOperand operand(const Act* a) {
@@ -1129,6 +1143,8 @@ struct Builder {
   }
 };
 
+static void build_launches(UNet* u, bool& ok);
+
 // params != null: build from a state_dict (record != 0: keep the packed blob, unet_blob_*); params == null: build from
 // `blob` (made by an earlier recording with the same dims / precision / layout version and a matching plan)
 static int unet_create_impl(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
@@ -1172,10 +1188,14 @@ static int unet_create_impl(const float* params, size_t n_params, const int* dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
       EDMP_CK(cudaFuncSetAttribute(conv_tc_kernel<TC_EL_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 10240));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
-      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 1, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
+      EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
       EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
       EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
@@ -1292,6 +1312,8 @@ static int unet_create_impl(const float* params, size_t n_params, const int* dim
     }
   }
 
+  build_launches(u, b.ok);
+
   // time-embedding table: TimeEmbedding (blocks.py:76-92) then each block's TimeMLP (:58-72)
   u->temb_width = b.temb_width;
   std::vector<float> table((size_t)kTSteps * b.temb_width);
@@ -1328,7 +1350,7 @@ static int unet_create_impl(const float* params, size_t n_params, const int* dim
     return 1;
   }
   u->play = nullptr;
-  u->n_launches = (int)u->layers.size() + (u->final_fused ? 0 : 1);
+  u->n_launches = (int)u->launches.size() + (u->final_fused ? 0 : 1);
   *out = u;
   return 0;
 }
@@ -1338,6 +1360,95 @@ void unet_destroy(UNet* u) {
   for (void* p : u->dev_allocs) cudaFree(p);
   delete u->rec;
   delete u;
+}
+
+
+// Shared-memory geometry of a run of conv_tc2 layers [first, first + n): one carve-up for all of them (the most demanding
+// layer decides).  Returns false when the layers cannot share a launch.
+static bool plan_run(const UNet* u, int first, int n, UNet::Launch* out) {
+  const Layer& l0 = u->layers[first];
+  const int nparts = u->tc_split ? 2 : 1;
+  const size_t a_stage = (size_t)kTcBlockBytes * nparts;
+  int max_slots = 0;
+  size_t part_bytes = 0, part_max = 0;   // weight bytes of one part of a stage (un-padded layout), GroupNorm piece area
+  for (int i = first; i < first + n; ++i) {
+    const Layer& ly = u->layers[i];
+    if (ly.kind != LAYER_TC2 || ly.cta_group != l0.cta_group || ly.b_pad != l0.b_pad || ly.t2.mma_warps != l0.t2.mma_warps)
+      return false;
+    if (n > 1 && ly.nsplit != 1) return false;                                   // column-split layers launch alone (their cluster)
+    if (l0.b_pad && (ly.t2_slot_bytes != l0.t2_slot_bytes || ly.t2_max_slots != l0.t2_max_slots)) return false;
+    max_slots = std::max(max_slots, ly.t2_max_slots);
+    part_bytes = std::max(part_bytes, (size_t)ly.t2_max_slots * ly.t2_slot_bytes);
+    part_max = std::max(part_max, ly.t2_part_bytes);
+  }
+  const size_t slot_bytes = l0.t2_slot_bytes;
+  auto b_bytes = [&](int k) {
+    return l0.b_pad ? (size_t)nparts * ((size_t)k * (max_slots + 1) + 1) * slot_bytes : (size_t)k * part_bytes * nparts;
+  };
+  const size_t budget = 232448 - 1024 - 7168 - part_max;   // dynamic limit - alignment slack - static shared memory - pieces
+  int bst = 0;
+  for (int k = 3; k >= 1 && !bst; --k)
+    if (b_bytes(k) + (size_t)std::max(2, std::min(k, 3)) * a_stage <= budget) bst = k;
+  if (!bst) return false;
+  const int ast = (int)std::min<size_t>(kT2MaxAStages, (budget - b_bytes(bst)) / a_stage);
+  if (ast < 2) return false;
+  out->first = first; out->n = n; out->run = true;
+  out->a_stages = ast; out->b_stages = bst;
+  if (l0.b_pad) {
+    out->b_stage_stride = (int)((max_slots + 1) * slot_bytes);
+    out->b_lo_off = (int)(((size_t)bst * (max_slots + 1) + 1) * slot_bytes);
+    out->b_real_off = (int)slot_bytes;
+    out->b_total_bytes = (int)(nparts * (size_t)out->b_lo_off);
+  } else {
+    out->b_stage_stride = (int)(part_bytes * nparts);
+    out->b_lo_off = (int)part_bytes;
+    out->b_real_off = 0;
+    out->b_total_bytes = (int)(bst * part_bytes * nparts);
+  }
+  out->slot_bytes = (int)slot_bytes;
+  out->smem = 1024 + (size_t)ast * a_stage + (size_t)out->b_total_bytes + part_max;
+  return true;
+}
+
+// Groups the layers of a forward into launch units: maximal runs of consecutive conv_tc2 layers that can share a
+// persistent launch (same cta_group, zero-slot layout and issuing warps; EDMP_NO_RUNS=1: one layer per launch).
+static void build_launches(UNet* u, bool& ok) {
+  // Runs need the row-tile chaining (the layers of a run synchronise through the progress counters only) and a batch
+  // that fills the machine: with fewer tiles than SMs, separate launches put consecutive layers on DIFFERENT idle SMs
+  // and overlap them completely, which one set of resident CTAs cannot (measured at 1020 rows: 2858 -> 2685 traj/s).
+  const bool runs = getenv("EDMP_NO_RUNS") == nullptr && u->chain;
+  const int rts = (u->max_rows + kTcRows - 1) / kTcRows;
+  auto fills = [&](const Layer& ly) { return (rts / ly.cta_group) * ly.t2.n_col_tiles >= u->sm_count / ly.cta_group; };
+  const int max_run = getenv("EDMP_MAX_RUN") ? std::max(1, std::min(kT2MaxRun, atoi(getenv("EDMP_MAX_RUN")))) : kT2MaxRun;
+  const int nl = (int)u->layers.size();
+  for (int i = 0; i < nl;) {
+    UNet::Launch L;
+    L.first = i; L.n = 1;
+    if (u->layers[i].kind == LAYER_TC2) {
+      int n = 1;
+      UNet::Launch best;
+      if (!plan_run(u, i, 1, &best)) { ok = false; return; }
+      // (a run is only extended while its layers stay chained: a conv_tc2 layer always follows a conv_tc2 layer here)
+      int own_a = u->layers[i].t2.a_stages, own_b = u->layers[i].t2.b_stages;   // fewest stages any layer of the run plans alone
+      while (runs && n < max_run && i + n < nl && u->layers[i + n].kind == LAYER_TC2 && fills(u->layers[i]) &&
+             fills(u->layers[i + n])) {
+        UNet::Launch cand;
+        if (!plan_run(u, i, n + 1, &cand)) break;
+        // a longer run must not cost stages: the shared carve-up has to give what the neediest layer gets alone
+        const int na = std::min(own_a, u->layers[i + n].t2.a_stages), nb = std::min(own_b, u->layers[i + n].t2.b_stages);
+        if (cand.a_stages < na || cand.b_stages < nb) break;
+        own_a = na; own_b = nb;
+        best = cand;
+        ++n;
+      }
+      L = best;
+    }
+    L.name = u->layers[L.first].name;
+    if (L.n > 1) L.name += " .. " + u->layers[L.first + L.n - 1].name + " (" + std::to_string(L.n) + " layers)";
+    for (int k = L.first; k < L.first + L.n; ++k) L.macs_per_row += u->layers[k].macs_per_row;
+    u->launches.push_back(L);
+    i += L.n;
+  }
 }
 
 int unet_create(const float* params, size_t n_params, const int* dims, int n_dims, int precision,
@@ -1396,6 +1507,68 @@ int unet_range_status(UNet* u, int* overflow, cudaStream_t st) {
 }
 int unet_launches(const UNet* u) { return u->n_launches; }
 
+template <int NR>
+static void launch_tc2(UNet* u, int cg, int cl, dim3 grid, size_t smem, cudaStream_t st, const Tc2RunT<NR>& r) {
+  if (cl > 1) {
+    if (u->tc_el == TC_EL_F16) {
+      if (cg == 2) launch_cluster(conv_tc2_kernel<TC_EL_F16, 2, NR>, grid, dim3(kT2Threads), smem, st, cl, r);
+      else launch_cluster(conv_tc2_kernel<TC_EL_F16, 1, NR>, grid, dim3(kT2Threads), smem, st, cl, r);
+    } else {
+      if (cg == 2) launch_cluster(conv_tc2_kernel<TC_EL_BF16, 2, NR>, grid, dim3(kT2Threads), smem, st, cl, r);
+      else launch_cluster(conv_tc2_kernel<TC_EL_BF16, 1, NR>, grid, dim3(kT2Threads), smem, st, cl, r);
+    }
+    return;
+  }
+  if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1, NR>, grid, dim3(kT2Threads), smem, st, r);
+  else launch_pdl(conv_tc2_kernel<TC_EL_BF16, 1, NR>, grid, dim3(kT2Threads), smem, st, r);
+}
+
+// one persistent launch over the conv_tc2 layers [L.first, L.first + L.n)
+static void run_tc2(UNet* u, const UNet::Launch& L, const float* temb_row, int rows, cudaStream_t st) {
+  static Tc2Run r;   // (7 KB: filled per launch; the library is single-threaded per handle)
+  const Layer& l0 = u->layers[L.first];
+  const int cg = l0.cta_group;
+  r.n = L.n;
+  r.a_stages = L.a_stages; r.b_stages = L.b_stages;
+  r.b_stage_stride = L.b_stage_stride; r.b_lo_off = L.b_lo_off; r.b_real_off = L.b_real_off; r.b_total_bytes = L.b_total_bytes;
+  r.b_pad = l0.b_pad; r.slot_bytes = L.slot_bytes;
+  r.mma_warps = l0.t2.mma_warps; r.split = u->tc_split ? 1 : 0;
+  int max_tiles = 0;
+  for (int k = 0; k < L.n; ++k) {
+    const Layer& ly = u->layers[L.first + k];
+    Tc2Args& a = r.l[k];
+    a = ly.t2;
+    a.rows = rows;
+    a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
+    a.dbg = u->dbg;
+    a.range_flag = u->range_flag;
+    a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
+    if (cg == 2) a.n_row_tiles = (a.n_row_tiles + 1) & ~1;
+    max_tiles = std::max(max_tiles, (a.n_row_tiles / cg) * a.n_col_tiles);
+  }
+  const int cl = cg == 2 ? 2 : l0.nsplit;                              // cluster size
+  const int walkers = std::min(max_tiles, u->sm_count / cl * cl / cg);   // CTA pairs (cg = 2) or CTAs that walk tiles
+  // the tiles of all layers of the run form one round-robin sequence over the walkers
+  long long g = 0;
+  for (int k = 0; k < L.n; ++k) {
+    r.rot[k] = (int)(g % walkers);
+    g += (r.l[k].n_row_tiles / cg) * r.l[k].n_col_tiles;
+  }
+  dim3 grid(walkers * cg);
+  if (L.n == 1) {
+    // single layer: the small kernel parameter
+    Tc2RunT<1> r1;
+    std::memcpy(&r1, &r, offsetof(Tc2Run, rot));
+    r1.rot[0] = 0;
+    r1.l[0] = r.l[0];
+    launch_tc2<1>(u, cg, cl, grid, L.smem, st, r1);
+    return;
+  }
+  launch_tc2<kT2MaxRun>(u, cg, cl, grid, L.smem, st, r);
+}
+
+static void run_launch(UNet* u, const UNet::Launch& L, const float* x, const float* temb_row, int rows, float* eps, cudaStream_t st);
+
 static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row, int rows, float* eps, cudaStream_t st) {
   const float* input_act = u->acts.at("input").p;
   if (ly.kind == LAYER_PM) {
@@ -1427,32 +1600,6 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     if (a.ra == input_act) a.ra = x;
     a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
     ly.fn(a, st);
-  } else if (ly.kind == LAYER_TC2) {
-    Tc2Args a = ly.t2;
-    a.rows = rows;
-    a.temb = ly.temb_off >= 0 ? temb_row + ly.temb_off : nullptr;
-    a.dbg = u->dbg;
-    a.range_flag = u->range_flag;
-    a.n_row_tiles = (rows + kTcRows - 1) / kTcRows;
-    if (ly.cta_group == 2) {
-      a.n_row_tiles = (a.n_row_tiles + 1) & ~1;
-      const int n_pair_tiles = (a.n_row_tiles / 2) * a.n_col_tiles;
-      dim3 grid(2 * std::min(n_pair_tiles, u->sm_count / 2));
-      if (u->tc_el == TC_EL_F16) launch_cluster(conv_tc2_kernel<TC_EL_F16, 2>, grid, dim3(kT2Threads), ly.tc_smem, st, 2, a);
-      else launch_cluster(conv_tc2_kernel<TC_EL_BF16, 2>, grid, dim3(kT2Threads), ly.tc_smem, st, 2, a);
-      return;
-    }
-    const int n_tiles = a.n_row_tiles * a.n_col_tiles;
-    if (ly.nsplit > 1) {
-      // clusters of nsplit CTAs walk neighbouring column tiles (one GroupNorm group) of the same row tile in lockstep
-      dim3 gridc(std::min(n_tiles, u->sm_count / ly.nsplit * ly.nsplit));
-      if (u->tc_el == TC_EL_F16) launch_cluster(conv_tc2_kernel<TC_EL_F16, 1>, gridc, dim3(kT2Threads), ly.tc_smem, st, ly.nsplit, a);
-      else launch_cluster(conv_tc2_kernel<TC_EL_BF16, 1>, gridc, dim3(kT2Threads), ly.tc_smem, st, ly.nsplit, a);
-      return;
-    }
-    dim3 grid(std::min(n_tiles, u->sm_count));
-    if (u->tc_el == TC_EL_F16) launch_pdl(conv_tc2_kernel<TC_EL_F16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
-    else launch_pdl(conv_tc2_kernel<TC_EL_BF16, 1>, grid, dim3(kT2Threads), ly.tc_smem, st, a);
   } else if (ly.kind == LAYER_TC) {
     TcArgs a = ly.targs;
     a.rows = rows;
@@ -1472,13 +1619,18 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
   }
 }
 
+static void run_launch(UNet* u, const UNet::Launch& L, const float* x, const float* temb_row, int rows, float* eps, cudaStream_t st) {
+  if (L.run) run_tc2(u, L, temb_row, rows, st);
+  else run_layer(u, u->layers[L.first], x, temb_row, rows, eps, st);
+}
+
 int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
   NvtxRange range("edmp_unet_forward");
   if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
-  for (Layer& ly : u->layers) run_layer(u, ly, x, temb_row, rows, eps, st);
+  for (const UNet::Launch& L : u->launches) run_launch(u, L, x, temb_row, rows, eps, st);
   if (!u->final_fused) {
     const int threads = 128;
     const size_t n = (size_t)rows * kHorizon;
@@ -1496,7 +1648,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
                  cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(iters > 0, "iters must be positive");
-  const int nl = (int)u->layers.size();
+  const int nl = (int)u->launches.size();
   const int n = nl + (u->final_fused ? 0 : 1);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) EDMP_CK(cudaEventCreate(&e));
@@ -1506,7 +1658,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
     if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
     EDMP_CK(cudaEventRecord(ev[0], st));
     for (int i = 0; i < nl; ++i) {
-      run_layer(u, u->layers[i], x, temb_row, rows, eps, st);
+      run_launch(u, u->launches[i], x, temb_row, rows, eps, st);
       EDMP_CK(cudaEventRecord(ev[i + 1], st));
     }
     if (!u->final_fused) {
@@ -1524,7 +1676,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
   }
   for (int i = 0; i < n; ++i) {
     ms[i] = (float)(acc[i] / iters);
-    macs[i] = i < nl ? u->layers[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
+    macs[i] = i < nl ? u->launches[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return 0;
@@ -1532,14 +1684,22 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
 
 // debug: run op `op` alone `iters` times and return the clock64 stamps of its CTAs ([ctas][8])
 int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int* n_ctas, cudaStream_t st) {
-  EDMP_REQUIRE(op >= 0 && op < (int)u->layers.size() &&
-                   (u->layers[op].kind == LAYER_TC || u->layers[op].kind == LAYER_PM || u->layers[op].kind == LAYER_TC2),
-               "op is not a tensor-core layer");
-  Layer& ly = u->layers[op];
-  const int ctas = ly.kind == LAYER_PM ? (u->pm2 ? std::min((rows + kPmRows - 1) / kPmRows, u->sm_count) : ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt))
-                   : ly.kind == LAYER_TC2 ? (ly.cta_group == 2 ? 2 * std::min(((((rows + kTcRows - 1) / kTcRows) + 1) / 2) * ly.t2.n_col_tiles, u->sm_count / 2)
-                                                               : std::min(((rows + kTcRows - 1) / kTcRows) * ly.t2.n_col_tiles, u->sm_count / ly.nsplit * ly.nsplit))
-                                          : ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
+  EDMP_REQUIRE(op >= 0 && op < (int)u->launches.size(), "no such launch");
+  const UNet::Launch& L = u->launches[op];
+  Layer& ly = u->layers[L.first];
+  EDMP_REQUIRE(ly.kind == LAYER_TC || ly.kind == LAYER_PM || ly.kind == LAYER_TC2, "op is not a tensor-core layer");
+  int ctas;
+  if (ly.kind == LAYER_PM) {
+    ctas = u->pm2 ? std::min((rows + kPmRows - 1) / kPmRows, u->sm_count) : ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt);
+  } else if (ly.kind == LAYER_TC2) {
+    const int cg = ly.cta_group, cl = cg == 2 ? 2 : ly.nsplit;
+    int rts = (rows + kTcRows - 1) / kTcRows, max_tiles = 0;
+    if (cg == 2) rts = (rts + 1) & ~1;
+    for (int k = 0; k < L.n; ++k) max_tiles = std::max(max_tiles, (rts / cg) * u->layers[L.first + k].t2.n_col_tiles);
+    ctas = std::min(max_tiles, u->sm_count / cl * cl / cg) * cg;
+  } else {
+    ctas = ((rows + kTcRows - 1) / kTcRows) * ly.tc_tiles;
+  }
   EDMP_REQUIRE(ctas <= max_ctas, "trace buffer too small");
   long long* d = nullptr;
   EDMP_CK(cudaMalloc(&d, (size_t)ctas * 16 * sizeof(long long)));
@@ -1548,7 +1708,13 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
   const float* temb_row = u->temb;
   float* eps_tmp = nullptr;
   if (ly.pm_final) EDMP_CK(cudaMalloc(&eps_tmp, (size_t)rows * kRowElems * sizeof(float)));
-  for (int it = 0; it < 3; ++it) run_layer(u, ly, u->acts.at("input").p, temb_row, rows, eps_tmp, st);
+  for (int it = 0; it < 3; ++it) {
+    // the run's own progress counters start from zero like in a forward (its first layer's producer counters keep the
+    // full counts of the last forward: no wait on a kernel that is not running)
+    if (u->tile_done && ly.kind == LAYER_TC2)
+      EDMP_CK(cudaMemsetAsync(u->tile_done + (size_t)L.first * u->tile_stride, 0, (size_t)L.n * u->tile_stride * sizeof(int), st));
+    run_launch(u, L, u->acts.at("input").p, temb_row, rows, eps_tmp, st);
+  }
   u->dbg = nullptr;
   EDMP_CK(cudaMemcpyAsync(out_h, d, (size_t)ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   EDMP_CK(cudaStreamSynchronize(st));
@@ -1559,14 +1725,14 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
 }
 
 const char* unet_op_name(const UNet* u, int i) {
-  if (i < 0 || i > (int)u->layers.size()) return nullptr;
-  return i == (int)u->layers.size() ? "final_conv.1" : u->layers[i].name.c_str();
+  if (i < 0 || i > (int)u->launches.size()) return nullptr;
+  return i == (int)u->launches.size() ? "final_conv.1" : u->launches[i].name.c_str();
 }
 
 const char* unet_op_kernel(const UNet* u, int i) {
-  if (i < 0 || i > (int)u->layers.size()) return nullptr;
-  if (i == (int)u->layers.size()) return "final_pw";
-  const Layer& ly = u->layers[i];
+  if (i < 0 || i > (int)u->launches.size()) return nullptr;
+  if (i == (int)u->launches.size()) return "final_pw";
+  const Layer& ly = u->layers[u->launches[i].first];
   switch (ly.kind) {
     case LAYER_TC2: return ly.cta_group == 2 ? "conv_tc2_pair" : "conv_tc2";
     case LAYER_TC: return "conv_tc";
