@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       // residual accumulator, identity-residual operand blocks) is issued first; the group statistics are combined
       // from the shared-memory pieces while those loads are in flight ----
 #pragma unroll 1
-      for (int kb = 0; kb < 4; ++kb) {
+      for (int kb = 0; kb < 8; ++kb) {   // (up to 16 units per tile with GroupNorm, up to 32 for a bias-only layer)
         if (part + 4 * kb >= n_units) break;
         uint32_t yr[1][16], rr[1][16];   // rr: residual accumulator, or the identity residual's hi (0..7) / lo (8..15) chunks
         float mean[1][2], rstd[1][2];

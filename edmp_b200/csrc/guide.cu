@@ -6,6 +6,7 @@
 // :637-653.  One CTA per trajectory row, one thread per waypoint (or segment); the scene's
 // obstacle boxes are staged once per CTA into shared memory.
 #include "common.cuh"
+#include "conv_pm.cuh"   // layout of the network's input image (pm_act_off, pm_img_bytes, kPmRows) and the hi / lo split
 #include "guide.h"
 #include "philox.cuh"
 
@@ -426,7 +427,32 @@ struct TailArgs {
   const unsigned char *method, *grad_norm;
   float* raw; double* rowsq;
   unsigned* bar; unsigned bar_target;
+  // network input image of the NEXT step (unet_input_image): written here instead of by a separate pack launch
+  void *pack_hi, *pack_lo;
+  int pack_el;                 // 0: no image (write the float32 copy xf), else TcEl of the engine
+  unsigned* range_flag;
 };
+
+// position l of one row into the position-major input image: 16 channels (7 joints + zeros), hi / lo halves -- the same
+// bits pm_pack_input_kernel (conv_pm.cuh) makes from the float32 copy
+template <int EL>
+__device__ __forceinline__ void pack_input_position(const TailArgs& a, int row, int l, const double* __restrict__ s_x, uint32_t& hmax) {
+  float w[8];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) w[j] = (float)s_x[j * kHorizon + l];
+  w[7] = 0.0f;
+  uint32_t h[4], r[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = pack16x2<EL>(w[2 * e], w[2 * e + 1]);
+    range_track<EL>(hmax, h[e]);
+    const float2 hf = unpack16x2<EL>(h[e]);
+    r[e] = pack16x2<EL>(w[2 * e] - hf.x, w[2 * e + 1] - hf.y);
+  }
+  const size_t off = (size_t)(row / kPmRows) * pm_img_bytes(kHorizon, 16) + pm_act_off(kHorizon, l, row % kPmRows, 0);
+  *reinterpret_cast<uint4*>((uint8_t*)a.pack_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (a.pack_lo) *reinterpret_cast<uint4*>((uint8_t*)a.pack_lo + off) = make_uint4(r[0], r[1], r[2], r[3]);
+}
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -442,6 +468,7 @@ __global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ T
   __shared__ float s_norm;
   __shared__ int s_norm_ens;
   constexpr int n_inner = kHorizon - 2;
+  uint32_t hmax = 0;   // largest |hi| half pattern written to the input image (operand range check, conv_tc.cuh)
   // (guided steps release the next kernel only after the barrier: its CTAs must not take the place of CTAs of this
   // grid that are not resident yet)
   if (!a.guided) pdl_launch_dependents();
@@ -459,9 +486,19 @@ __global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ T
       if (a.condition && l == kHorizon - 1) v = a.goal[j];
       s_x[e] = v;
       a.x[i] = v;
-      a.xf[i] = (float)v;
+      if (!a.pack_el) a.xf[i] = (float)v;
     }
-    if (!a.guided) continue;
+    if (!a.guided) {
+      if (a.pack_el) {
+        __syncthreads();
+        if (threadIdx.x < kHorizon) {
+          if (a.pack_el == TC_EL_F16) pack_input_position<TC_EL_F16>(a, row, threadIdx.x, s_x, hmax);
+          else pack_input_position<TC_EL_BF16>(a, row, threadIdx.x, s_x, hmax);
+        }
+        __syncthreads();   // the next row overwrites s_x
+      }
+      continue;
+    }
     stage_obstacles(a.sc, true, a.expansion[(size_t)row * kTSteps + a.t - 1], a.clearance[(size_t)row * kTSteps + a.t - 1],
                     s_omin, s_omax);
     __syncthreads();
@@ -482,7 +519,10 @@ __global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ T
     __syncthreads();   // (also: every thread is done with s_x and the obstacle boxes of this row)
     if (threadIdx.x == 0) a.rowsq[row] = s_red[0] + s_red[1];
   }
-  if (!a.guided) return;
+  if (!a.guided) {
+    if (a.pack_el == TC_EL_F16) range_report<TC_EL_F16>(hmax, a.range_flag);
+    return;
+  }
 
   // ---- grid-wide barrier: every row's raw gradient and sum of squares is written ----
   __syncthreads();
@@ -523,17 +563,30 @@ __global__ void __launch_bounds__(64) step_tail_kernel(const __grid_constant__ T
     const float norm = s_norm;  // np.linalg.norm of a float32 array is float32
     const double gn = a.grad_norm[row] ? 1.0 : 0.0;
     const double scale = a.schedule[(size_t)row * kTSteps + a.t - 1];
-    for (int e = threadIdx.x; e < 7 * n_inner; e += 64) {
-      const float G = a.raw[(size_t)row * 7 * n_inner + e];
-      // float32 division, float64 mix -- 0/0 = NaN poisons every row of the ensemble like the reference
-      const double mixed = (1.0 - gn) * (double)G + gn * (double)(G / norm);
-      const int j = e / n_inner, w = e % n_inner;
-      const size_t idx = (size_t)row * kRowElems + j * kHorizon + 1 + w;
-      const double v = a.x[idx] - scale * mixed;
-      a.x[idx] = v;
-      a.xf[idx] = (float)v;
+    for (int e = threadIdx.x; e < kRowElems; e += 64) {
+      const int j = e / kHorizon, l = e % kHorizon;
+      const size_t idx = (size_t)row * kRowElems + e;
+      double v = a.x[idx];
+      if (l >= 1 && l <= n_inner) {
+        const float G = a.raw[((size_t)row * 7 + j) * n_inner + (l - 1)];
+        // float32 division, float64 mix -- 0/0 = NaN poisons every row of the ensemble like the reference
+        const double mixed = (1.0 - gn) * (double)G + gn * (double)(G / norm);
+        v -= scale * mixed;
+        a.x[idx] = v;
+        if (!a.pack_el) a.xf[idx] = (float)v;
+      }
+      s_x[e] = v;
+    }
+    if (a.pack_el) {
+      __syncthreads();
+      if (threadIdx.x < kHorizon) {
+        if (a.pack_el == TC_EL_F16) pack_input_position<TC_EL_F16>(a, row, threadIdx.x, s_x, hmax);
+        else pack_input_position<TC_EL_BF16>(a, row, threadIdx.x, s_x, hmax);
+      }
+      __syncthreads();   // the next row overwrites s_x
     }
   }
+  if (a.pack_el == TC_EL_F16) range_report<TC_EL_F16>(hmax, a.range_flag);
 }
 
 // ---- full volume tensors for the cost()/swept_volume_cost() API --------------------------------
@@ -760,7 +813,8 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
 // start of a pass; *bar_epoch counts the guided steps since then.
 int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, const double* noise, uint64_t seed, int t,
                            double c1, double sqrt_alpha, double beta, const double* start_h, const double* goal_h,
-                           int rows, bool guided, bool condition, unsigned* bar, unsigned* bar_epoch, cudaStream_t st) {
+                           int rows, bool guided, bool condition, unsigned* bar, unsigned* bar_epoch, void* pack_hi,
+                           void* pack_lo, int pack_el, unsigned* range_flag, cudaStream_t st) {
   EDMP_REQUIRE(s->rows == rows, "guide tables were set for a different row count");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t out of range");
   if (guided && ensure_work(s, rows, kHorizon - 2)) return 1;
@@ -785,6 +839,7 @@ int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, con
   a.method = s->method; a.grad_norm = s->grad_norm;
   a.raw = s->raw; a.rowsq = s->rowsq;
   a.bar = bar;
+  a.pack_hi = pack_hi; a.pack_lo = pack_lo; a.pack_el = pack_hi ? pack_el : 0; a.range_flag = range_flag;
   if (guided) { *bar_epoch += 1; a.bar_target = *bar_epoch * (unsigned)grid; }
   launch_pdl(step_tail_kernel, dim3(grid), dim3(64), 0, st, a);
   EDMP_CK(cudaGetLastError());

@@ -46,7 +46,8 @@ int guide_gradient_launch(Scene* s, const double* x, int ld, int off, int n_inne
 // posterior + (guided steps) gradient, norm mix, guided update, endpoints, float32 copy: one launch per reverse step
 int guide_step_tail_launch(Scene* s, double* x, float* xf, const float* eps, const double* noise, uint64_t seed, int t,
                            double c1, double sqrt_alpha, double beta, const double* start_h, const double* goal_h,
-                           int rows, bool guided, bool condition, unsigned* bar, unsigned* bar_epoch, cudaStream_t st);
+                           int rows, bool guided, bool condition, unsigned* bar, unsigned* bar_epoch, void* pack_hi,
+                           void* pack_lo, int pack_el, unsigned* range_flag, cudaStream_t st);
 int guide_volumes_launch(Scene* s, const float* q, const double* start_h, const double* goal_h, int t,
                          int mode, int rows, int n, float* vol, cudaStream_t st);
 int guide_final_cost_launch(Scene* s, const double* traj, const double* start_h, const double* goal_h,

@@ -139,13 +139,19 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
   const bool fused = scene != nullptr && !split_tail;
   unsigned bar_epoch = 0;
   if (fused) EDMP_CK(cudaMemsetAsync(s->bar, 0, sizeof(unsigned), st));
+  // the fused tail also writes the network's input image of the next step (no separate pack launch from step 2 on)
+  void *pack_hi = nullptr, *pack_lo = nullptr;
+  int pack_el = 0;
+  unsigned* range_flag = nullptr;
+  const bool fold = fused && unet_input_image(u, &pack_hi, &pack_lo, &pack_el, &range_flag);
+  bool packed = false;   // the image holds the current state (written by the previous step's tail)
   condition_kernel<<<blocks, threads, 0, st>>>(x, s->xf, sc, s->condition, n);
   ++launches;
   for (int t = t_start; t > t_stop; --t) {
     snprintf(label, sizeof(label), "step t=%d%s", t, (scene && (t % 2) == 0 && t >= 5) ? " (guided)" : "");
     NvtxRange step_range(label);
-    if (unet_forward(u, s->xf, t, rows, s->eps, st)) return 1;
-    launches += unet_launches(u);
+    if (packed ? unet_forward_packed(u, t, rows, s->eps, st) : unet_forward(u, s->xf, t, rows, s->eps, st)) return 1;
+    launches += unet_launches(u) - (packed ? 1 : 0);
     const double a = s->alpha[t - 1], ab = s->alpha_bar[t - 1];
     sc.c1 = (1 - a) / std::sqrt(1 - ab);
     sc.sqrt_alpha = std::sqrt(a);
@@ -154,9 +160,11 @@ int sample_guided(Sampler* s, UNet* u, Scene* scene, double* x, const double* st
     if (fused) {
       // guidance cadence: (t % 2) < 1 and t >= 5  (diffusion.py:326-327)
       if (guide_step_tail_launch(scene, x, s->xf, s->eps, z, seed, t, sc.c1, sc.sqrt_alpha, sc.beta, start, goal, rows,
-                                 (t % 2) == 0 && t >= 5, s->condition, s->bar, &bar_epoch, st))
+                                 (t % 2) == 0 && t >= 5, s->condition, s->bar, &bar_epoch, fold ? pack_hi : nullptr,
+                                 pack_lo, pack_el, range_flag, st))
         return 1;
       ++launches;
+      packed = fold;
       continue;
     }
     launch_pdl(posterior_kernel, dim3(blocks), dim3(threads), 0, st, x, s->xf, (const float*)s->eps, z, seed, t, ens, sc, s->condition, n);

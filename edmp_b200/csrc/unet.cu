@@ -621,7 +621,9 @@ struct Builder {
     }
     t.stage_bytes = (int)((stage_total + 1023) & ~(size_t)1023);
     ly.tc_smem = 1024 + t.stage_bytes + 1024;
-    if (u->tc2 && !t.out_plain && t.lout * t.ct <= 16 * kT2MaxUnits) finish_tc2_layer(ly, n_tiles);   // (25-position up-sampling stays on v1)
+    // (bias-only layers may take all 512 accumulator columns, single-buffered: the 13 -> 25 up-sampling has 25 x 16 = 400)
+    const int max_cols = (t.mode == TC_BIAS && getenv("EDMP_UP3_V1") == nullptr) ? 512 : 16 * kT2MaxUnits;
+    if (u->tc2 && !t.out_plain && t.lout * t.ct <= max_cols) finish_tc2_layer(ly, n_tiles);
   }
 
   // persistent kernel (conv_tc2.cuh): same operand layouts and weight tiles as conv_tc.cuh
@@ -650,7 +652,7 @@ struct Builder {
     }
     v.lout = t.lout; v.ct = t.ct; v.cout = t.cout; v.cg = t.cg; v.mode = t.mode; v.split = u->tc_split ? 1 : 0;
     const int cols = t.lout * t.ct;
-    ok = ok && cols <= 16 * kT2MaxUnits && (cols % 16) == 0 && t.ct <= 128;
+    ok = ok && cols <= (t.mode == TC_BIAS ? 512 : 16 * kT2MaxUnits) && (cols % 16) == 0 && t.ct <= 128;
     v.acc_bufs = ((t.n_phases == 1 && cols <= 256) || (t.n_phases == 2 && cgrp == 1 && t.ph[1].d_col + cols <= 256)) ? 2 : 1;
     v.acc_stride = 256;
     v.half_layout = cgrp == 2 ? 1 : 0;
@@ -1624,13 +1626,25 @@ static void run_launch(UNet* u, const UNet::Launch& L, const float* x, const flo
   else run_layer(u, u->layers[L.first], x, temb_row, rows, eps, st);
 }
 
-int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st) {
+bool unet_input_image(UNet* u, void** hi, void** lo, int* el, unsigned** range_flag) {
+  if (u->launches.empty() || u->layers[0].kind != LAYER_PM_PACK || getenv("EDMP_NO_PACK_FOLD") != nullptr) return false;
+  *hi = u->layers[0].pack_dst.phi;
+  *lo = u->layers[0].pack_dst.plo;
+  *el = u->tc_el;
+  *range_flag = u->range_flag;
+  return true;
+}
+
+static int unet_forward_impl(UNet* u, const float* x, int t, int rows, float* eps, bool packed, cudaStream_t st) {
   EDMP_REQUIRE(rows > 0 && rows <= u->max_rows, "rows exceeds the workspace (max_rows)");
   EDMP_REQUIRE(t >= 1 && t <= kTSteps, "t must be in 1..255");
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
   NvtxRange range("edmp_unet_forward");
   if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
-  for (const UNet::Launch& L : u->launches) run_launch(u, L, x, temb_row, rows, eps, st);
+  for (const UNet::Launch& L : u->launches) {
+    if (packed && u->layers[L.first].kind == LAYER_PM_PACK) continue;   // the input image is already in place
+    run_launch(u, L, x, temb_row, rows, eps, st);
+  }
   if (!u->final_fused) {
     const int threads = 128;
     const size_t n = (size_t)rows * kHorizon;
@@ -1640,6 +1654,14 @@ int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStrea
   }
   EDMP_CK(cudaGetLastError());
   return 0;
+}
+
+int unet_forward(UNet* u, const float* x, int t, int rows, float* eps, cudaStream_t st) {
+  return unet_forward_impl(u, x, t, rows, eps, false, st);
+}
+int unet_forward_packed(UNet* u, int t, int rows, float* eps, cudaStream_t st) {
+  EDMP_REQUIRE(!u->launches.empty() && u->layers[0].kind == LAYER_PM_PACK, "this engine has no packed input image");
+  return unet_forward_impl(u, nullptr, t, rows, eps, true, st);
 }
 
 // Per-op device time (CUDA events around every launch on the launching stream), averaged over
