@@ -5,6 +5,10 @@ The reference picks ``argmin`` of the per-row t=0 swept-volume cost over ONE ens
 whole ensembles stay rank-local -- so the per-step whole-ensemble gradient norm (lib/guide.py:629)
 never crosses ranks -- and the only exchange is an all-gather of the per-row final costs, after
 which every rank knows the best row of every ensemble.
+
+Seeding: device noise is Philox with the rank-LOCAL element index as the counter, so ranks that pass the same ``seed`` to
+``Diffusion.run_steps`` / ``denoise_guided(noise="philox")`` draw identical per-step noise for equal row indices (only
+x_T would differ).  Give every rank its own stream, e.g. ``seed = pass_index * world_size + rank`` (bench.py does).
 """
 import torch
 import torch.distributed as dist

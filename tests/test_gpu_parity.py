@@ -397,6 +397,28 @@ def test_sampler_properties_full_batch(model02):
     assert np.array_equal(best, out[int(np.argmin(costs))])
 
 
+def test_sampler_refuses_a_scene_without_guide_tables(model02):
+    """edmp_sample_guided with a scene whose per-row tables were never set (or set for another row count) is an error
+    with a message, not a read of unset device pointers."""
+    import ctypes
+    from edmp_b200 import Diffusion, IntersectionVolumeGuide, _lib
+    lib = _lib.load()
+    cfgs = _cfgs((1, 2), 2)
+    guide = IntersectionVolumeGuide(scenes.tabletop_scene(), DEV, cfgs, 4)
+    diff = Diffusion(255, DEV)
+    x = torch.zeros(4, 7, 50, dtype=torch.float64, device=DEV)
+    s_arr, s_ptr = _lib.host_f64(scenes.START)
+    g_arr, g_ptr = _lib.host_f64(scenes.GOAL)
+    rc = lib.edmp_sample_guided(diff._sampler(4), model02.engine(4), guide._scene_handle(), ctypes.c_void_p(x.data_ptr()),
+                                s_ptr, g_ptr, None, ctypes.c_uint64(0), 4, 255, 254, None, _lib.stream_ptr())
+    assert rc != 0 and b"guide tables" in lib.edmp_last_error()
+    guide.scene_handle(rows=4)                       # tables for 4 rows ...
+    x6 = torch.zeros(6, 7, 50, dtype=torch.float64, device=DEV)
+    rc = lib.edmp_sample_guided(diff._sampler(6), model02.engine(6), guide._scene_handle(), ctypes.c_void_p(x6.data_ptr()),
+                                s_ptr, g_ptr, None, ctypes.c_uint64(0), 6, 255, 254, None, _lib.stream_ptr())
+    assert rc != 0 and b"guide tables" in lib.edmp_last_error()     # ... do not serve a 6-row call
+
+
 def test_philox_noise_statistics(model02):
     """Device-side N(0,1): unguided steps with eps-free check is not possible, so look at the
     increment of one posterior step with and without noise."""

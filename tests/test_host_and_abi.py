@@ -249,3 +249,19 @@ def test_sparc_oracle_properties():
     np.testing.assert_allclose(mo.sparc(3.7 * bell, 50.)[0], a, rtol=1e-12)
     np.testing.assert_allclose(mo.sparc((bell + 0.2 * t)[::-1], 50.)[0], mo.sparc(bell + 0.2 * t, 50.)[0], rtol=1e-9)
     assert mo.sparc(wobble, 50.)[0] < a < 0
+
+
+def test_obstacle_cap_is_an_error_not_a_truncation():
+    """EDMP_MAX_OBSTACLES (64) is a hard cap of the scene tables: a larger scene is refused with a message (before any
+    CUDA call, so this runs without a GPU), never silently truncated."""
+    import ctypes
+    from edmp_b200 import _lib
+    lib = _lib.load()
+    cfg = np.zeros((65, 10))
+    cfg[:, 6] = 1.0
+    cfg[:, 7:] = 0.1
+    h = ctypes.c_void_p()
+    rc = lib.edmp_scene_create(cfg.ctypes.data_as(ctypes.c_void_p), 65, None, ctypes.byref(h))
+    assert rc != 0 and b"1..64" in lib.edmp_last_error()
+    rc = lib.edmp_scene_create(cfg.ctypes.data_as(ctypes.c_void_p), 0, None, ctypes.byref(h))
+    assert rc != 0

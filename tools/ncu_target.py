@@ -16,7 +16,7 @@ rows_per_guide = int(sys.argv[1]) // 10 if len(sys.argv) > 1 else 103
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 precision = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 dev = "cuda:0"
-cfgs, scene, x_T, start, goal = bench.build_workload(0, rows_per_guide)
+cfgs, scene, x_T, start, goal = bench.build_workload(bench.CONFIGS["c2"]["guides"], rows_per_guide)
 rows = cfgs["total_batch_size"]
 model = TemporalUNet(os.path.join(tempfile.mkdtemp(), "m"), 7, 32, dev, dims=(32, 64, 128, 256, 512, 512),
                      precision=precision)
