@@ -12,8 +12,18 @@
 //     epilogues are always in flight next to the load + MMA of the following block.
 // Reference ops covered: as conv_pm.cuh (Conv1dBlock blocks.py:13-34, ResidualConvolutionBlock :137-166, the stride-2
 // Conv1d :211, ConvTranspose1d :249, final_conv temporalunet.py:35-36).
+//
+// PAIR = 1 (round 2, opt-in with EDMP_PM_PAIR=1): cta_group::2.  Hypothesis: the kernel is bound by the NUMBER of MMAs it
+// issues (120 per row block whatever the channel count: ~80 cycles each against 16-32 of tensor time at N = 32 / 64).
+// Measured: it is not -- every layer got ~5 us SLOWER (8190 rows: 63.8 -> 68.0 us for down_samplers.0.down.0.blocks.0);
+// ncu shows the epilogue groups' instruction issue as the limiter (issue slots 43 % busy, 18 warps per SM, long-scoreboard
+// and barrier stalls), so halving the MMAs only adds the cluster launch.  Kept as a tested variant.  A CTA pair walks DOUBLE blocks: each
+// CTA stages its own row block's image and half of the layer's weight rows, the leader issues M = 256 MMAs for both
+// (half the MMAs per row block), the peer relays its "image full" barrier, the leader's commits multicast "image empty" /
+// "accumulator full" to both CTAs, and both CTAs' epilogue groups release the accumulator buffer on the leader's barrier.
 #pragma once
 #include "conv_pm.cuh"
+#include "conv_tc2.cuh"   // t2:: cluster / cta_group::2 helpers
 
 namespace edmp {
 
@@ -32,7 +42,7 @@ constexpr int kPm2MaxIssue = 128;
 __device__ __forceinline__ void pm2_group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kPmEpiThreads) : "memory"); }
 
 // CG = channels per GroupNorm group (4: C_out = 32, 8: C_out = 64); the CTA computes all C_out = 8 * CG channels.
-template <int EL, int CG>
+template <int EL, int CG, int PAIR>
 __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_constant__ PmArgs a) {
   static_assert(EL != TC_EL_TF32, "position-major kernels use 16-bit operand elements");
   constexpr int COUT = 8 * CG;
@@ -42,6 +52,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_w, bar_a_full, bar_a_empty, bar_acc_full[kPm2Groups], bar_acc_empty[kPm2Groups];
+  __shared__ uint64_t pw_full, pa_full;      // PAIR, leader: "the peer's weights / image are in"
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_par[5 * 64];       // bias | gamma | beta | temb | aux bias
   __shared__ float s_fw[7 * 64 + 8];                  // final 1x1 conv weights + bias
@@ -57,6 +68,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   const int nparts = a.split ? 2 : 1;
   const int ntiles = (a.n_m + 15) >> 4;
   const int n_blocks = (a.rows + kPmRows - 1) / kPmRows;
+  // walk units: row blocks, or double blocks of a CTA pair (rank r of pair u holds row block 2u + r; the odd tail block's
+  // partner re-reads the last block and stores nothing)
+  constexpr int NC = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? t2::cluster_ctarank() : 0u;
+  const int n_units = (n_blocks + NC - 1) / NC;
+  const int unit0 = blockIdx.x / NC, n_walkers = gridDim.x / NC;
+  const int w_part_cta = a.w_bytes_part / NC;                    // this CTA's share of one weight part (half of the rows of every slot)
   const int acc_cols = (a.n_groups + a.aux) * ntiles * COUT;     // accumulator columns of one block (<= 256)
   uint8_t* a_smem = smem;                                        // [part][source] images
   uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][COUT rows][rby]
@@ -68,11 +86,18 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     umma::mbar_init(&bar_w, 1);
     umma::mbar_init(&bar_a_full, 1);
     umma::mbar_init(&bar_a_empty, 1);
-    for (int g = 0; g < kPm2Groups; ++g) { umma::mbar_init(bar_acc_full + g, 1); umma::mbar_init(bar_acc_empty + g, kPmEpiWarps); }
+    for (int g = 0; g < kPm2Groups; ++g) { umma::mbar_init(bar_acc_full + g, 1); umma::mbar_init(bar_acc_empty + g, kPmEpiWarps * NC); }
+    umma::mbar_init(&pw_full, 1);
+    umma::mbar_init(&pa_full, 1);
     umma::fence_barrier_init();
   }
   if (warp == 1) {
-    umma::tmem_alloc<512>(&tmem_slot);
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(&tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      umma::tmem_alloc<512>(&tmem_slot);
+    }
     // issue table: entry e = (M tile, term, K chunk, 32-byte K step)
     const uint32_t a_base = umma::smem_u32(a_smem), w_base = umma::smem_u32(w_smem);
     const int ksteps = C >> 4;
@@ -83,13 +108,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       uint32_t seen = 0;
       for (int tj = 0; tj < ti; ++tj) seen |= (a.terms[tj].acc == t.acc) ? 1u : 0u;
       const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * 128);
-      const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * COUT * rby);
+      const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * (COUT / NC) * rby);
       const uint32_t lbo = (uint32_t)(a.lin + 4) * 128u, ka = (uint32_t)ks * (lbo >> 3);   // K step = two 16-byte chunks
       PmIssue it;
       it.da_hi = (uint32_t)(umma::make_desc_interleaved(a_addr, lbo, a.stride * 128) + ka);
       it.da_lo = (uint32_t)(umma::make_desc_interleaved(a_addr + (uint32_t)(nkc * a.a_bytes_img), lbo, a.stride * 128) + ka);
       it.db_hi = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);
-      it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)a.w_bytes_part, atom, rby) + 2 * ks);
+      it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)w_part_cta, atom, rby) + 2 * ks);
       it.d_off = (uint32_t)((t.acc * ntiles + mt) * COUT);
       it.acc = (seen | (uint32_t)(kc > 0) | (uint32_t)(ks > 0)) ? 1u : 0u;
       it.pad0 = it.pad1 = 0;
@@ -111,18 +136,29 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (PAIR) t2::cluster_sync_all();
   umma::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
     // ===== producer: weights once (they do not depend on the previous kernel), then one activation image per block =====
     if (lane == 0) {
-      umma::mbar_arrive_expect_tx(&bar_w, (uint32_t)(nparts * a.w_bytes_part));
-      for (int p = 0; p < nparts; ++p)
-        umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, (const uint8_t*)(p ? a.w_lo : a.w_hi), (uint32_t)a.w_bytes_part, &bar_w);
+      umma::mbar_arrive_expect_tx(&bar_w, (uint32_t)(nparts * w_part_cta));
+      if (PAIR) {
+        // this CTA's half of the rows (output channels) of every (slot, K chunk) block of the weight image
+        const int blk = COUT * rby, n_sub = a.w_bytes_part / blk;
+        for (int p = 0; p < nparts; ++p)
+          for (int sb = 0; sb < n_sub; ++sb)
+            umma::bulk_g2s(w_smem + (size_t)p * w_part_cta + (size_t)sb * (blk / 2),
+                           (const uint8_t*)(p ? a.w_lo : a.w_hi) + (size_t)sb * blk + (size_t)rank * (blk / 2), (uint32_t)(blk / 2), &bar_w);
+      } else {
+        for (int p = 0; p < nparts; ++p)
+          umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, (const uint8_t*)(p ? a.w_lo : a.w_hi), (uint32_t)a.w_bytes_part, &bar_w);
+      }
       pdl_wait();   // activations of the previous kernel are read below
       uint32_t ph = 0;
-      for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+      for (int un = unit0; un < n_units; un += n_walkers) {
+        const int rb = min(un * NC + (int)rank, n_blocks - 1);
         umma::mbar_wait(&bar_a_empty, ph ^ 1);     // the MMAs of the previous block have read the image
         umma::mbar_arrive_expect_tx(&bar_a_full, (uint32_t)(nparts * nkc * a.a_bytes_img));
         for (int p = 0; p < nparts; ++p)
@@ -134,21 +170,35 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         ph ^= 1;
       }
     }
+  } else if (warp == 1 && PAIR && rank == 1) {
+    // ===== peer of a CTA pair: relay "my weights / my image are in" to the leader, which issues the MMAs for both =====
+    umma::mbar_wait(&bar_w, 0);
+    if (lane == 0) t2::mbar_arrive_remote(&pw_full, 0);
+    __syncwarp();
+    uint32_t ph = 0;
+    for (int un = unit0; un < n_units; un += n_walkers) {
+      umma::mbar_wait(&bar_a_full, ph);
+      if (lane == 0) t2::mbar_arrive_remote(&pa_full, 0);
+      __syncwarp();
+      ph ^= 1;
+    }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
     umma::mbar_wait(&bar_w, 0);
-    const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128, COUT);
+    if (PAIR) umma::mbar_wait(&pw_full, 0);
+    const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128 * NC, COUT);
     const int n_issue = ntiles * a.n_terms * nkc * (C >> 4);
     const uint64_t hi_a = umma::make_desc_interleaved(0, 0, a.stride * 128) & 0xFFFFFFFF00000000ull;   // SBO, version, no swizzle
     const uint64_t hi_b = pm_desc(0, atom, rby) & 0xFFFFFFFF00000000ull;
     uint32_t ph = 0, k = 0;
     long long w_acc = 0, w_a = 0, t_begin = dbg ? clock64() : 0;
-    for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x, ++k) {
+    for (int un = unit0; un < n_units; un += n_walkers, ++k) {
       const uint32_t g = k & 1, use = k >> 1;
       long long tw = dbg ? clock64() : 0;
-      umma::mbar_wait(bar_acc_empty + g, (use & 1) ^ 1);      // the group has drained this accumulator buffer
+      umma::mbar_wait(bar_acc_empty + g, (use & 1) ^ 1);      // the group(s) have drained this accumulator buffer
       if (dbg) { const long long t1 = clock64(); w_acc += t1 - tw; tw = t1; }
       umma::mbar_wait(&bar_a_full, ph);
+      if (PAIR) umma::mbar_wait(&pa_full, ph);
       if (dbg) w_a += clock64() - tw;
       ph ^= 1;
       umma::tc_fence_after();
@@ -158,7 +208,15 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         const PmIssue nxt = s_issue[e + 1 < n_issue ? e + 1 : e];   // prefetch: the issue below blocks for ~40 cycles per MMA
         const uint32_t d = acc0 + cur.d_off;
         if (umma::elect_one()) {
-          if (a.split) {
+          if (PAIR) {
+            if (a.split) {
+              t2::mma_f16_cg2(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
+              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
+              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, 1u);
+            } else {
+              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, cur.acc);
+            }
+          } else if (a.split) {
             umma::mma_bf16(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
             umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
             umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, 1u);
@@ -170,8 +228,9 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         cur = nxt;
       }
       if (umma::elect_one()) {
-        umma::mma_commit(&bar_a_empty);          // the image may be overwritten once these MMAs have read it
-        umma::mma_commit(bar_acc_full + g);
+        // the image may be overwritten once these MMAs have read it (PAIR: in both CTAs)
+        if (PAIR) { t2::commit_cg2(&bar_a_empty); t2::commit_cg2(bar_acc_full + g); }
+        else { umma::mma_commit(&bar_a_empty); umma::mma_commit(bar_acc_full + g); }
       }
       __syncwarp();
     }
@@ -192,8 +251,9 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     uint32_t k = (uint32_t)grp;
     long long w_full = 0, t_busy = 0, t_stats = 0;
     uint32_t hmax = 0;   // largest |hi| half pattern stored (operand range check, conv_tc.cuh)
-    for (int rb = blockIdx.x + grp * gridDim.x; rb < n_blocks; rb += kPm2Groups * gridDim.x, k += kPm2Groups) {
+    for (int un = unit0 + grp * n_walkers; un < n_units; un += kPm2Groups * n_walkers, k += kPm2Groups) {
       const uint32_t use = k >> 1;
+      const int rb = un * NC + (int)rank;         // (past the batch for the odd tail's partner: nothing is stored)
       const int grow = rb * kPmRows + row;        // global trajectory row
       const long long tw0 = dbg ? clock64() : 0;
       umma::mbar_wait(bar_acc_full + grp, use & 1);
@@ -362,7 +422,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       // every accumulator read of this block is complete: hand the buffer back to the MMA warp
       umma::tc_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(bar_acc_empty + grp);
+      if (lane == 0) { if (PAIR && rank == 1) t2::mbar_arrive_remote(bar_acc_empty + grp, 0); else umma::mbar_arrive(bar_acc_empty + grp); }
       if (dbg) t_busy += clock64() - t_start;
     }
     range_report<EL>(hmax, a.range_flag);
@@ -370,9 +430,11 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     umma::tc_fence_before();
   }
   __syncthreads();
+  if (PAIR) t2::cluster_sync_all();
   if (warp == 1) {
     umma::tc_fence_after();
-    umma::tmem_dealloc<512>(tmem_base);
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else umma::tmem_dealloc<512>(tmem_base);
   }
   if (dbg && threadIdx.x == 0) { dbg[1] = dbg[0]; dbg[7] = clock64(); }
 }

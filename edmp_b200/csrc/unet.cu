@@ -240,6 +240,7 @@ struct UNet {
   bool tc2 = false;           // persistent second-generation kernel (conv_tc2.cuh) for the rows-as-M levels
   bool cg2 = false;           // CTA pairs (cta_group::2) for the horizon 2 / 4 levels (large batches)
   bool pm2 = false;           // persistent position-major kernel (conv_pm2.cuh): one CTA per SM, all output channels per CTA
+  bool pm_pair = false;       // conv_pm2 with cta_group::2: CTA pairs walk double row blocks (half the MMAs per block)
   bool chain = false;         // row-tile chaining between consecutive conv_tc2 launches (conv_tc2.cuh)
   bool narrow = false;        // small batches: narrower column tiles / column-split GroupNorm groups (more tiles per layer)
   int* tile_done = nullptr;   // [layer][row tile] progress counters, zeroed at the start of every forward
@@ -1198,10 +1199,14 @@ static int unet_create_impl(const float* params, size_t n_params, const int* dim
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 1, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_F16, 2, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
       EDMP_CK(cudaFuncSetAttribute(conv_tc2_kernel<TC_EL_BF16, 2, kT2MaxRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7168));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
-      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_F16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
+      EDMP_CK(cudaFuncSetAttribute(conv_pm2_kernel<TC_EL_BF16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 13312));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
       EDMP_CK(cudaFuncSetAttribute(conv_pm_kernel<TC_EL_BF16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144 - 1024));
@@ -1222,6 +1227,9 @@ static int unet_create_impl(const float* params, size_t n_params, const int* dim
   u->pm = u->tc && u->tc_16() && getenv("EDMP_NO_PM") == nullptr;
   u->tc2 = u->pm && getenv("EDMP_TC_V1") == nullptr;
   u->pm2 = u->pm && getenv("EDMP_PM_V1") == nullptr;
+  // (opt-in: measured 5 us per layer SLOWER at 8190 and at 1020 rows -- the position-major layers are bound by their
+  // epilogues' instruction issue, not by the number of MMAs; DESIGN.md round log)
+  u->pm_pair = u->pm2 && getenv("EDMP_PM_PAIR") != nullptr;
   // pairs halve the number of schedulable tiles: only worth it when the batch still fills the machine
   u->cg2 = u->tc2 && getenv("EDMP_NO_CG2") == nullptr && (max_rows >= 4096 || getenv("EDMP_CG2") != nullptr);
   u->narrow = u->tc2 && getenv("EDMP_NO_NARROW") == nullptr;
@@ -1581,9 +1589,17 @@ static void run_layer(UNet* u, Layer& ly, const float* x, const float* temb_row,
     a.dbg = u->dbg;
     a.range_flag = u->range_flag;
     if (u->pm2) {
-      dim3 grid2(std::min((rows + kPmRows - 1) / kPmRows, u->sm_count));
-      auto k2 = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm2_kernel<TC_EL_F16, 4> : conv_pm2_kernel<TC_EL_F16, 8>)
-                                      : (a.cout == 32 ? conv_pm2_kernel<TC_EL_BF16, 4> : conv_pm2_kernel<TC_EL_BF16, 8>);
+      const int n_blocks = (rows + kPmRows - 1) / kPmRows;
+      if (u->pm_pair) {
+        dim3 gridp(2 * std::min((n_blocks + 1) / 2, u->sm_count / 2));
+        auto kp = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm2_kernel<TC_EL_F16, 4, 1> : conv_pm2_kernel<TC_EL_F16, 8, 1>)
+                                        : (a.cout == 32 ? conv_pm2_kernel<TC_EL_BF16, 4, 1> : conv_pm2_kernel<TC_EL_BF16, 8, 1>);
+        launch_cluster(kp, gridp, dim3(kPm2Threads), ly.tc_smem, st, 2, a);
+        return;
+      }
+      dim3 grid2(std::min(n_blocks, u->sm_count));
+      auto k2 = u->tc_el == TC_EL_F16 ? (a.cout == 32 ? conv_pm2_kernel<TC_EL_F16, 4, 0> : conv_pm2_kernel<TC_EL_F16, 8, 0>)
+                                      : (a.cout == 32 ? conv_pm2_kernel<TC_EL_BF16, 4, 0> : conv_pm2_kernel<TC_EL_BF16, 8, 0>);
       launch_pdl(k2, grid2, dim3(kPm2Threads), ly.tc_smem, st, a);
       return;
     }
@@ -1712,7 +1728,8 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
   EDMP_REQUIRE(ly.kind == LAYER_TC || ly.kind == LAYER_PM || ly.kind == LAYER_TC2, "op is not a tensor-core layer");
   int ctas;
   if (ly.kind == LAYER_PM) {
-    ctas = u->pm2 ? std::min((rows + kPmRows - 1) / kPmRows, u->sm_count) : ((rows + kPmRows - 1) / kPmRows) * (ly.pargs.cout / kPmCt);
+    const int nb = (rows + kPmRows - 1) / kPmRows;
+    ctas = u->pm_pair ? 2 * std::min((nb + 1) / 2, u->sm_count / 2) : u->pm2 ? std::min(nb, u->sm_count) : nb * (ly.pargs.cout / kPmCt);
   } else if (ly.kind == LAYER_TC2) {
     const int cg = ly.cta_group, cl = cg == 2 ? 2 : ly.nsplit;
     int rts = (rows + kTcRows - 1) / kTcRows, max_tiles = 0;
