@@ -13,14 +13,16 @@
 // Reference ops covered: as conv_pm.cuh (Conv1dBlock blocks.py:13-34, ResidualConvolutionBlock :137-166, the stride-2
 // Conv1d :211, ConvTranspose1d :249, final_conv temporalunet.py:35-36).
 //
-// PAIR = 1 (round 2, opt-in with EDMP_PM_PAIR=1): cta_group::2.  Hypothesis: the kernel is bound by the NUMBER of MMAs it
-// issues (120 per row block whatever the channel count: ~80 cycles each against 16-32 of tensor time at N = 32 / 64).
-// Measured: it is not -- every layer got ~5 us SLOWER (8190 rows: 63.8 -> 68.0 us for down_samplers.0.down.0.blocks.0);
-// ncu shows the epilogue groups' instruction issue as the limiter (issue slots 43 % busy, 18 warps per SM, long-scoreboard
-// and barrier stalls), so halving the MMAs only adds the cluster launch.  Kept as a tested variant.  A CTA pair walks DOUBLE blocks: each
-// CTA stages its own row block's image and half of the layer's weight rows, the leader issues M = 256 MMAs for both
-// (half the MMAs per row block), the peer relays its "image full" barrier, the leader's commits multicast "image empty" /
-// "accumulator full" to both CTAs, and both CTAs' epilogue groups release the accumulator buffer on the leader's barrier.
+// PAIR = 1 (round 2, opt-in with EDMP_PM_PAIR=1): cta_group::2 -- a CTA pair walks DOUBLE row blocks with M = 256 MMAs
+// (half the MMAs per row block), and the two CTAs ALTERNATE as the issuer (unit k is led by CTA k & 1, which is also the
+// accumulator buffer / epilogue group k & 1; the odd CTA of a pair may issue cta_group::2 MMAs).  Each CTA stages its own
+// row block's image and half of the layer's weight rows, the non-leading CTA relays its "image full" barrier, the
+// leader's commits multicast "image empty" / "accumulator full" to both CTAs, both CTAs' epilogue groups release buffer g
+// on CTA g's barrier.  Hypotheses tested: the kernel is bound (a) by the NUMBER of MMAs it issues, (b) by the issue rate
+// of one warp per SM.  Measured: neither -- every layer is 4-6 us SLOWER with pairs, with and without alternating
+// leadership (8190 rows: 64.5 -> 68.3 us for down_samplers.0.down.0.blocks.0).  What binds the MMA warp (busy ~90k of a
+// layer's 110k cycles) is the shared-memory fetch of the A operand: 4 KB per M = 128 MMA (+1-2 KB of B at N = 32 / 64) is
+// 40-48 cycles at 128 B/clk, paid by each of the three split products, and a pair does not share A.  Kept as a tested variant.
 #pragma once
 #include "conv_pm.cuh"
 #include "conv_tc2.cuh"   // t2:: cluster / cta_group::2 helpers
@@ -170,22 +172,17 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         ph ^= 1;
       }
     }
-  } else if (warp == 1 && PAIR && rank == 1) {
-    // ===== peer of a CTA pair: relay "my weights / my image are in" to the leader, which issues the MMAs for both =====
-    umma::mbar_wait(&bar_w, 0);
-    if (lane == 0) t2::mbar_arrive_remote(&pw_full, 0);
-    __syncwarp();
-    uint32_t ph = 0;
-    for (int un = unit0; un < n_units; un += n_walkers) {
-      umma::mbar_wait(&bar_a_full, ph);
-      if (lane == 0) t2::mbar_arrive_remote(&pa_full, 0);
-      __syncwarp();
-      ph ^= 1;
-    }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform walk, one elected lane issues) =====
+    // PAIR: the two CTAs ALTERNATE as the issuer of the pair's M = 256 MMAs (unit k is led by CTA k & 1 -- which is also
+    // the accumulator buffer / epilogue group k & 1): the kernel is bound by the issue rate of ONE warp per SM
+    // (~27 cycles per MMA at N = 32), so the pair must issue from both SMs to halve the time, not only the count.
     umma::mbar_wait(&bar_w, 0);
-    if (PAIR) umma::mbar_wait(&pw_full, 0);
+    if (PAIR) {
+      if (lane == 0) t2::mbar_arrive_remote(&pw_full, rank ^ 1u);   // "my weights are in"
+      __syncwarp();
+      umma::mbar_wait(&pw_full, 0);
+    }
     const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128 * NC, COUT);
     const int n_issue = ntiles * a.n_terms * nkc * (C >> 4);
     const uint64_t hi_a = umma::make_desc_interleaved(0, 0, a.stride * 128) & 0xFFFFFFFF00000000ull;   // SBO, version, no swizzle
@@ -194,11 +191,19 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
     long long w_acc = 0, w_a = 0, t_begin = dbg ? clock64() : 0;
     for (int un = unit0; un < n_units; un += n_walkers, ++k) {
       const uint32_t g = k & 1, use = k >> 1;
+      if (PAIR && g != rank) {
+        // the peer leads this unit: tell it that my image is in
+        umma::mbar_wait(&bar_a_full, ph);
+        if (lane == 0) t2::mbar_arrive_remote(&pa_full, rank ^ 1u);
+        __syncwarp();
+        ph ^= 1;
+        continue;
+      }
       long long tw = dbg ? clock64() : 0;
       umma::mbar_wait(bar_acc_empty + g, (use & 1) ^ 1);      // the group(s) have drained this accumulator buffer
       if (dbg) { const long long t1 = clock64(); w_acc += t1 - tw; tw = t1; }
       umma::mbar_wait(&bar_a_full, ph);
-      if (PAIR) umma::mbar_wait(&pa_full, ph);
+      if (PAIR) umma::mbar_wait(&pa_full, use & 1);           // (one relay per unit I lead)
       if (dbg) w_a += clock64() - tw;
       ph ^= 1;
       umma::tc_fence_after();
@@ -422,7 +427,8 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       // every accumulator read of this block is complete: hand the buffer back to the MMA warp
       umma::tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (PAIR && rank == 1) t2::mbar_arrive_remote(bar_acc_empty + grp, 0); else umma::mbar_arrive(bar_acc_empty + grp); }
+      // (PAIR: buffer / group g is led -- and waited for -- by CTA g of the pair)
+      if (lane == 0) { if (PAIR && rank != (uint32_t)grp) t2::mbar_arrive_remote(bar_acc_empty + grp, (uint32_t)grp); else umma::mbar_arrive(bar_acc_empty + grp); }
       if (dbg) t_busy += clock64() - t_start;
     }
     range_report<EL>(hmax, a.range_flag);

@@ -22,6 +22,12 @@ x = torch.randn(rows, 7, 50, device=dev)
 eps = m(x, 100)
 torch.cuda.synchronize()
 print("forward ok", float(eps.abs().max()))
+if len(sys.argv) > 2 and sys.argv[2] == "unet":     # large batches: the multi-layer persistent runs, UNet only
+    eps2 = m(x, 100)
+    torch.cuda.synchronize()
+    assert torch.equal(eps, eps2)
+    print("runs ok (bit-reproducible)")
+    sys.exit(0)
 hp = load_guide_hparams([1, 10, 9], os.path.join(ROOT, "guides") + "/")
 cfgs = build_guide_cfgs(hp, 2)
 guide = IntersectionVolumeGuide(synthetic.tabletop_scene(), dev, cfgs, cfgs["total_batch_size"])
