@@ -83,6 +83,12 @@ struct PmArgs {
   int rows;
   long long* dbg;                   // optional [ctas][8] clock64 stamps (tools/tc_trace.py), normally null
   unsigned* range_flag;             // set when a stored IEEE-half hi part is infinite (conv_tc.cuh range_track), may be null
+  // conv_pm2, split modes: 1 = TWO MMAs per K step instead of three.  The kernel is bound by the shared-memory fetch of
+  // the A operand (4 KB per M = 128 MMA whatever N is), so x_hi is fetched once for BOTH of its products: the weight
+  // rows of a (slot, K chunk) block sit as [lo rows | hi rows] and x_hi * [w_lo ; w_hi] is one MMA of N = 2 C_out into
+  // the column pair [D_a | D_b]; x_lo * w_hi adds into D_b; the epilogue reads D_a + D_b.  Needs 2 x the accumulator
+  // columns (<= 256 per buffer), so layers with an aux group keep the three-MMA form.
+  int fuse_b;
 };
 
 __device__ __forceinline__ uint64_t pm_desc(uint32_t smem_addr, int sbo_bytes, int rby) {

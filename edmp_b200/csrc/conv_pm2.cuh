@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   const int n_units = (n_blocks + NC - 1) / NC;
   const int unit0 = blockIdx.x / NC, n_walkers = gridDim.x / NC;
   const int w_part_cta = a.w_bytes_part / NC;                    // this CTA's share of one weight part (half of the rows of every slot)
-  const int acc_cols = (a.n_groups + a.aux) * ntiles * COUT;     // accumulator columns of one block (<= 256)
+  const int FB = (a.fuse_b && !PAIR) ? 2 : 1;                    // accumulator columns per output channel ([D_a | D_b], PmArgs::fuse_b)
+  const int acc_cols = (a.n_groups + a.aux) * ntiles * COUT * FB;   // accumulator columns of one block (<= 256)
   uint8_t* a_smem = smem;                                        // [part][source] images
   uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][COUT rows][rby]
 
@@ -110,14 +111,20 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       uint32_t seen = 0;
       for (int tj = 0; tj < ti; ++tj) seen |= (a.terms[tj].acc == t.acc) ? 1u : 0u;
       const uint32_t a_addr = a_base + (uint32_t)(kc * a.a_bytes_img + (a.stride * 16 * mt + t.off) * 128);
-      const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * (COUT / NC) * rby);
+      // weight rows of this (slot, K chunk): COUT / NC rows per part; fuse_b: [lo rows | hi rows] back to back
+      const uint32_t w_addr = w_base + (uint32_t)((t.slot * nkc + kc) * (COUT / NC) * rby * FB);
       const uint32_t lbo = (uint32_t)(a.lin + 4) * 128u, ka = (uint32_t)ks * (lbo >> 3);   // K step = two 16-byte chunks
       PmIssue it;
       it.da_hi = (uint32_t)(umma::make_desc_interleaved(a_addr, lbo, a.stride * 128) + ka);
       it.da_lo = (uint32_t)(umma::make_desc_interleaved(a_addr + (uint32_t)(nkc * a.a_bytes_img), lbo, a.stride * 128) + ka);
-      it.db_hi = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);
-      it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)w_part_cta, atom, rby) + 2 * ks);
-      it.d_off = (uint32_t)((t.acc * ntiles + mt) * COUT);
+      if (FB == 2) {
+        it.db_lo = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);                          // [lo | hi]: the N = 2 C_out operand starts at lo
+        it.db_hi = (uint32_t)(pm_desc(w_addr + (uint32_t)(COUT * rby), atom, rby) + 2 * ks);  // the hi rows alone
+      } else {
+        it.db_hi = (uint32_t)(pm_desc(w_addr, atom, rby) + 2 * ks);
+        it.db_lo = (uint32_t)(pm_desc(w_addr + (uint32_t)w_part_cta, atom, rby) + 2 * ks);
+      }
+      it.d_off = (uint32_t)((t.acc * ntiles + mt) * COUT * FB);
       it.acc = (seen | (uint32_t)(kc > 0) | (uint32_t)(ks > 0)) ? 1u : 0u;
       it.pad0 = it.pad1 = 0;
       s_issue[e] = it;
@@ -153,6 +160,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
           for (int sb = 0; sb < n_sub; ++sb)
             umma::bulk_g2s(w_smem + (size_t)p * w_part_cta + (size_t)sb * (blk / 2),
                            (const uint8_t*)(p ? a.w_lo : a.w_hi) + (size_t)sb * blk + (size_t)rank * (blk / 2), (uint32_t)(blk / 2), &bar_w);
+      } else if (FB == 2) {
+        // [lo rows | hi rows] per (slot, K chunk) block
+        const int blk = COUT * rby, n_sub = a.w_bytes_part / blk;
+        for (int sb = 0; sb < n_sub; ++sb) {
+          umma::bulk_g2s(w_smem + (size_t)sb * 2 * blk, (const uint8_t*)a.w_lo + (size_t)sb * blk, (uint32_t)blk, &bar_w);
+          umma::bulk_g2s(w_smem + (size_t)sb * 2 * blk + blk, (const uint8_t*)a.w_hi + (size_t)sb * blk, (uint32_t)blk, &bar_w);
+        }
       } else {
         for (int p = 0; p < nparts; ++p)
           umma::bulk_g2s(w_smem + (size_t)p * a.w_bytes_part, (const uint8_t*)(p ? a.w_lo : a.w_hi), (uint32_t)a.w_bytes_part, &bar_w);
@@ -184,6 +198,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       umma::mbar_wait(&pw_full, 0);
     }
     const uint32_t idesc = umma::make_idesc(TcElem<EL>::kFmt, 128 * NC, COUT);
+    const uint32_t idesc2 = umma::make_idesc(TcElem<EL>::kFmt, 128, 2 * COUT);   // fuse_b: x_hi * [w_lo ; w_hi]
     const int n_issue = ntiles * a.n_terms * nkc * (C >> 4);
     const uint64_t hi_a = umma::make_desc_interleaved(0, 0, a.stride * 128) & 0xFFFFFFFF00000000ull;   // SBO, version, no swizzle
     const uint64_t hi_b = pm_desc(0, atom, rby) & 0xFFFFFFFF00000000ull;
@@ -221,6 +236,10 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
             } else {
               t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, cur.acc);
             }
+          } else if (FB == 2) {
+            // [D_a | D_b] (+)= x_hi * [w_lo ; w_hi] first (one accumulate flag for both halves), then D_b += x_lo * w_hi
+            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc2, cur.acc);
+            umma::mma_bf16(d + (uint32_t)COUT, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, 1u);
           } else if (a.split) {
             umma::mma_bf16(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
             umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
@@ -282,7 +301,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
 #pragma unroll
             for (int u = 0; u < UNITS; ++u) {
               float v[16], b[16];
-              umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT + u * 16), v);
+              umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT * FB + u * 16), v);
+              if (FB == 2) {
+                float v1[16];
+                umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT * FB + COUT + u * 16), v1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += v1[i];
+              }
               pm_ld_par16(s_par + u * 16, b);
               if (valid) {
 #pragma unroll
@@ -339,7 +364,13 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
             float v[16];
-            umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT + u * 16), v);
+            umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT * FB + u * 16), v);
+            if (FB == 2) {
+              float v1[16];
+              umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT * FB + COUT + u * 16), v1);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += v1[i];
+            }
             // identity residual (blocks.py:164): issue the loads before the arithmetic that hides their latency
             uint4 rh[2], rl[2];
             const bool res = valid && !is_aux && a.mode == PM_GN_RES;

@@ -945,6 +945,9 @@ struct Builder {
     const int ntiles = (t.n_m + 15) / 16;
     int cols = (t.n_groups + t.aux) * ntiles * pct, p2 = 32;
     while (p2 < cols) p2 *= 2;
+    // two-MMA form of the split product (PmArgs::fuse_b): needs twice the accumulator columns inside a 256-column buffer
+    t.fuse_b = (u->pm2 && u->tc_split && !u->pm_pair && 2 * cols <= 256 && getenv("EDMP_NO_PM_FUSEB") == nullptr) ? 1 : 0;
+    if (t.fuse_b) { cols *= 2; p2 = 32; while (p2 < cols) p2 *= 2; }
     t.tmem_cols = p2;
     if (p2 > (u->pm2 ? 256 : 512)) { ok = false; why += " pm:tmem(" + ly.name + ")"; }   // (persistent kernel: two accumulator buffers of 256 columns)
     if (u->pm2 && ntiles * t.n_terms * nkc * (C / 16) > kPm2MaxIssue) { ok = false; why += " pm:issue-table(" + ly.name + ")"; }

@@ -149,7 +149,7 @@ def test_unet_headline_batch_matches_small_batch(tmp_path_factory, sd):
         assert (few - small(x[:5].contiguous().to(DEV), 200)).abs().max().item() <= 2e-5
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16x3", 5e-5), ("f16", 3e-2), ("bf16", 2e-1)])
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 7e-5), ("f16", 3e-2), ("bf16", 2e-1)])
 def test_unet_other_16bit_modes_run_the_same_kernels(tmp_path_factory, sd, prec, tol, monkeypatch):
     """The throughput-only arithmetic modes share the persistent kernels (BF16 elements, single-pass = no lo parts):
     they must run (also on the CTA-pair path) and stay within their own, looser, distance of the oracle."""
