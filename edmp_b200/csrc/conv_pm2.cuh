@@ -43,6 +43,47 @@ constexpr int kPm2MaxIssue = 128;
 
 __device__ __forceinline__ void pm2_group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kPmEpiThreads) : "memory"); }
 
+
+// The issue loop of one row block, run by ONE elected thread (no per-entry elect / branch / reconvergence, the arithmetic
+// mode is a compile-time constant, the next table entry is fetched while the current MMAs issue).  Ablation traces
+// (tools/gpu_ablate.sh, profiles/r2_ablation_8190rows.txt): with the epilogue idle the warp-uniform loop with a per-entry
+// elect took ~200 cycles per table entry against ~90 of MMA time (N = 64 + N = 32) -- the issue loop, not the tensor
+// pipe, bound the MMA warp.  MODE 0: one product, 1: three split products, 2: two-MMA form (PmArgs::fuse_b).
+template <int MODE, int PAIR>
+__device__ __forceinline__ void pm2_issue_block(const PmIssue* tab, int n_issue, uint32_t acc0, uint64_t hi_a, uint64_t hi_b,
+                                                uint32_t idesc, uint32_t idesc2, uint32_t cout) {
+  uint4 c0 = *reinterpret_cast<const uint4*>(tab);                 // da_hi, da_lo, db_hi, db_lo
+  uint2 c1 = *reinterpret_cast<const uint2*>(&tab->d_off);         // d_off, acc
+#pragma unroll 2
+  for (int e = 0; e < n_issue; ++e) {
+    const PmIssue* nx = tab + (e + 1 < n_issue ? e + 1 : e);
+    const uint4 n0 = *reinterpret_cast<const uint4*>(nx);
+    const uint2 n1 = *reinterpret_cast<const uint2*>(&nx->d_off);
+    const uint32_t d = acc0 + c1.x;
+    const uint64_t a_hi = hi_a | c0.x, a_lo = hi_a | c0.y, b_hi = hi_b | c0.z, b_lo = hi_b | c0.w;
+    if (PAIR) {
+      if (MODE == 1) {
+        t2::mma_f16_cg2(d, a_lo, b_hi, idesc, c1.y);
+        t2::mma_f16_cg2(d, a_hi, b_lo, idesc, 1u);
+        t2::mma_f16_cg2(d, a_hi, b_hi, idesc, 1u);
+      } else {
+        t2::mma_f16_cg2(d, a_hi, b_hi, idesc, c1.y);
+      }
+    } else if (MODE == 2) {
+      // [D_a | D_b] (+)= x_hi * [w_lo ; w_hi] first (one accumulate flag for both halves), then D_b += x_lo * w_hi
+      umma::mma_bf16(d, a_hi, b_lo, idesc2, c1.y);
+      umma::mma_bf16(d + cout, a_lo, b_hi, idesc, 1u);
+    } else if (MODE == 1) {
+      umma::mma_bf16(d, a_lo, b_hi, idesc, c1.y);
+      umma::mma_bf16(d, a_hi, b_lo, idesc, 1u);
+      umma::mma_bf16(d, a_hi, b_hi, idesc, 1u);
+    } else {
+      umma::mma_bf16(d, a_hi, b_hi, idesc, c1.y);
+    }
+    c0 = n0; c1 = n1;
+  }
+}
+
 // CG = channels per GroupNorm group (4: C_out = 32, 8: C_out = 64); the CTA computes all C_out = 8 * CG channels.
 template <int EL, int CG, int PAIR>
 __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_constant__ PmArgs a) {
@@ -83,6 +124,7 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
   uint8_t* w_smem = smem + ((a.a_bytes_total + 1023) & ~1023);   // [part][slot][kc][COUT rows][rby]
 
   long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  const int ablate = dbg ? g_edmp_ablate : 0;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -223,35 +265,11 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       ph ^= 1;
       umma::tc_fence_after();
       const uint32_t acc0 = tmem_base + g * 256u;
-      PmIssue cur = s_issue[0];
-      for (int e = 0; e < n_issue; ++e) {
-        const PmIssue nxt = s_issue[e + 1 < n_issue ? e + 1 : e];   // prefetch: the issue below blocks for ~40 cycles per MMA
-        const uint32_t d = acc0 + cur.d_off;
-        if (umma::elect_one()) {
-          if (PAIR) {
-            if (a.split) {
-              t2::mma_f16_cg2(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
-              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
-              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, 1u);
-            } else {
-              t2::mma_f16_cg2(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, cur.acc);
-            }
-          } else if (FB == 2) {
-            // [D_a | D_b] (+)= x_hi * [w_lo ; w_hi] first (one accumulate flag for both halves), then D_b += x_lo * w_hi
-            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc2, cur.acc);
-            umma::mma_bf16(d + (uint32_t)COUT, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, 1u);
-          } else if (a.split) {
-            umma::mma_bf16(d, hi_a | cur.da_lo, hi_b | cur.db_hi, idesc, cur.acc);
-            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_lo, idesc, 1u);
-            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, 1u);
-          } else {
-            umma::mma_bf16(d, hi_a | cur.da_hi, hi_b | cur.db_hi, idesc, cur.acc);
-          }
-        }
-        __syncwarp();
-        cur = nxt;
-      }
       if (umma::elect_one()) {
+        const int n_e = (ablate & 2) ? 0 : n_issue;
+        if (FB == 2) pm2_issue_block<2, PAIR>(s_issue, n_e, acc0, hi_a, hi_b, idesc, idesc2, (uint32_t)COUT);
+        else if (a.split) pm2_issue_block<1, PAIR>(s_issue, n_e, acc0, hi_a, hi_b, idesc, idesc2, (uint32_t)COUT);
+        else pm2_issue_block<0, PAIR>(s_issue, n_e, acc0, hi_a, hi_b, idesc, idesc2, (uint32_t)COUT);
         // the image may be overwritten once these MMAs have read it (PAIR: in both CTAs)
         if (PAIR) { t2::commit_cg2(&bar_a_empty); t2::commit_cg2(bar_acc_full + g); }
         else { umma::mma_commit(&bar_a_empty); umma::mma_commit(bar_acc_full + g); }
@@ -286,51 +304,107 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
       const long long t_start = dbg ? clock64() : 0;
       if (dbg) w_full += t_start - tw0;
 
+      if (ablate & 1) {
+        umma::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_acc_empty + grp);
+        continue;
+      }
+      // M tiles of this warp: mt = half + 2 * ti; an (M tile, lane quarter) whose 4 positions all lie past n_m is skipped by
+      // the whole warp (horizon 50: 3 of 16, horizon 25: 1 of 8 -- the MMAs computed zero-image positions there)
+      auto tile_live = [&](int mt) { return mt < ntiles && 16 * mt + quarter * 4 < a.n_m; };
+      // one accumulator unit (16 columns of M tile mt, accumulator group g_acc) -> raw fp32 values; fuse_b: D_a + D_b.
+      // Two units (or the two halves of a fuse_b unit) are in flight per wait.
+      auto ld_unit_pair = [&](int g_acc, int mt, int u, uint32_t (&x0)[16], uint32_t (&x1)[16]) {
+        const uint32_t base = t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT * FB + u * 16);
+        t2::tmem_ld16_nowait(base, x0);
+        t2::tmem_ld16_nowait(base + (uint32_t)(FB == 2 ? COUT : 16), x1);
+      };
+
       if (a.mode != PM_BIAS) {
-        // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26), two-pass
+        // GroupNorm(8, C) over (CG channels x lout positions) of a row (blocks.py:24-26).  ONE pass over the accumulator:
+        // a thread reduces the CG channels of a group at its position to an exact two-pass (sum, M2) piece in registers;
+        // the row's mean comes from the sums, then M2 = sum_pieces M2_p + CG * (mean_p - mean)^2 (no E[x^2] - mean^2
+        // cancellation, the same decomposition as conv_tc2's pieces) -- two small reductions, no second accumulator read.
         const float inv_n = 1.0f / (float)(CG * a.n_m);
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          // (dense fp32 math in packed f32x2 form, see umma.cuh f2::; a pair of neighbouring channels shares its group)
-          f2::f32x2 s2[NG];
+        constexpr float kInvCg = 1.0f / (float)CG;
+        float S[2][NG], Q[2][NG], nv[2];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) s2[g] = f2::dup(0.0f);
-          const f2::f32x2 sc2 = f2::dup(a.acc_scale);
-          for (int mt = half; mt < ntiles; mt += 2) {
-            const bool valid = (16 * mt + pos_in_tile) < a.n_m;
+        for (int ti = 0; ti < 2; ++ti) {
+          nv[ti] = 0.0f;
+#pragma unroll
+          for (int g = 0; g < NG; ++g) { S[ti][g] = 0.0f; Q[ti][g] = 0.0f; }
+        }
+        const f2::f32x2 sc2 = f2::dup(a.acc_scale);
+        auto stats_unit = [&](int ti, int u, const uint32_t (&x)[16], const uint32_t* x_add) {
+          float b[16];
+          pm_ld_par16(s_par + u * 16, b);
+          f2::f32x2 y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0 = __uint_as_float(x[2 * i]), v1 = __uint_as_float(x[2 * i + 1]);
+            if (x_add) { v0 += __uint_as_float(x_add[2 * i]); v1 += __uint_as_float(x_add[2 * i + 1]); }
+            y[i] = f2::fma(f2::pk(v0, v1), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
+          }
+#pragma unroll
+          for (int k = 0; k < GPU_; ++k) {
+            constexpr int PP = CG / 2;             // packed pairs per group
+            f2::f32x2 t = y[k * PP];
+#pragma unroll
+            for (int i = 1; i < PP; ++i) t = f2::add(t, y[k * PP + i]);
+            const float sum = f2::hsum(t);
+            const f2::f32x2 m2 = f2::dup(sum * kInvCg);
+            f2::f32x2 q = f2::dup(0.0f);
+#pragma unroll
+            for (int i = 0; i < PP; ++i) { const f2::f32x2 d = f2::sub(y[k * PP + i], m2); q = f2::fma(d, d, q); }
+            S[ti][u * GPU_ + k] = sum;
+            Q[ti][u * GPU_ + k] = f2::hsum(q);
+          }
+        };
+#pragma unroll
+        for (int ti = 0; ti < 2; ++ti) {
+          const int mt = half + 2 * ti;
+          if (!tile_live(mt)) continue;
+          uint32_t x0[16], x1[16];
+          if (FB == 2) {
 #pragma unroll
             for (int u = 0; u < UNITS; ++u) {
-              float v[16], b[16];
-              umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT * FB + u * 16), v);
-              if (FB == 2) {
-                float v1[16];
-                umma::tmem_ld16(t_lane + (uint32_t)(mt * COUT * FB + COUT + u * 16), v1);
+              ld_unit_pair(0, mt, u, x0, x1);
+              t2::tmem_ld_wait();
+              stats_unit(ti, u, x0, x1);
+            }
+          } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += v1[i];
-              }
-              pm_ld_par16(s_par + u * 16, b);
-              if (valid) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int g = u * GPU_ + (2 * i) / CG;
-                  const f2::f32x2 y = f2::fma(f2::pk(v[2 * i], v[2 * i + 1]), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
-                  if (pass == 0) s2[g] = f2::add(s2[g], y);
-                  else { const f2::f32x2 d = f2::sub(y, f2::dup(mr[0][row][g])); s2[g] = f2::fma(d, d, s2[g]); }
-                }
-              }
+            for (int u = 0; u < UNITS; u += 2) {
+              ld_unit_pair(0, mt, u, x0, x1);
+              t2::tmem_ld_wait();
+              stats_unit(ti, u, x0, nullptr);
+              stats_unit(ti, u + 1, x1, nullptr);
             }
           }
-          float s[NG];
+          if ((16 * mt + pos_in_tile) < a.n_m) nv[ti] = (float)CG;
+          else {
 #pragma unroll
-          for (int g = 0; g < NG; ++g) s[g] = f2::hsum(s2[g]);
+            for (int g = 0; g < NG; ++g) { S[ti][g] = 0.0f; Q[ti][g] = 0.0f; }
+          }
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          float r8[NG];
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
-            s[g] += __shfl_xor_sync(0xffffffffu, s[g], 8);
-            s[g] += __shfl_xor_sync(0xffffffffu, s[g], 16);
+            if (pass == 0) r8[g] = S[0][g] + S[1][g];
+            else {
+              const float mean = mr[0][row][g];
+              const float d0 = S[0][g] * kInvCg - mean, d1 = S[1][g] * kInvCg - mean;
+              r8[g] = fmaf(nv[0] * d0, d0, Q[0][g]) + fmaf(nv[1] * d1, d1, Q[1][g]);
+            }
+            r8[g] += __shfl_xor_sync(0xffffffffu, r8[g], 8);
+            r8[g] += __shfl_xor_sync(0xffffffffu, r8[g], 16);
           }
           if (lane < 8) {
 #pragma unroll
-            for (int g = 0; g < NG; ++g) red[ew][row][g] = s[g];
+            for (int g = 0; g < NG; ++g) red[ew][row][g] = r8[g];
           }
           pm2_group_barrier(grp);
           if (et < 8 * NG) {
@@ -354,41 +428,28 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
         void* o_hi = is_aux ? a.aux_hi : a.out_hi;
         void* o_lo = is_aux ? a.aux_lo : a.out_lo;
         for (int mt = half; mt < ntiles; mt += 2) {
+          if (!tile_live(mt)) continue;
           const int idx = 16 * mt + pos_in_tile;
           const bool valid = idx < a.n_m && grow < a.rows;
           const int lo = is_aux ? idx : a.out_step * idx + a.out_off[g_acc];     // output position
           const size_t img = (size_t)rb * pm_img_bytes(a.lout, a.cout);                   // this row block's image
+          const bool res = valid && !is_aux && a.mode == PM_GN_RES;
           f2::f32x2 fin2[7];
 #pragma unroll
           for (int j = 0; j < 7; ++j) fin2[j] = f2::dup(0.0f);
-#pragma unroll
-          for (int u = 0; u < UNITS; ++u) {
-            float v[16];
-            umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT * FB + u * 16), v);
-            if (FB == 2) {
-              float v1[16];
-              umma::tmem_ld16(t_lane + (uint32_t)((g_acc * ntiles + mt) * COUT * FB + COUT + u * 16), v1);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += v1[i];
-            }
-            // identity residual (blocks.py:164): issue the loads before the arithmetic that hides their latency
-            uint4 rh[2], rl[2];
-            const bool res = valid && !is_aux && a.mode == PM_GN_RES;
-            if (res) {
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                const size_t off = img + pm_act_off(a.lout, lo, row, 2 * u + m);
-                rh[m] = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
-                rl[m] = a.res.lo ? *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off) : make_uint4(0, 0, 0, 0);
-              }
-            }
+          // one 16-channel unit: raw accumulator values (+ the second fuse_b half) -> output chunks
+          auto final_unit = [&](int u, const uint32_t (&x)[16], const uint32_t* x_add, const uint4 (&rh)[2], const uint4 (&rl)[2]) {
             f2::f32x2 v2[8];
             {
               float b[16];
               pm_ld_par16(pb + u * 16, b);
               const f2::f32x2 sc2 = f2::dup(sc);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v2[i] = f2::fma(f2::pk(v[2 * i], v[2 * i + 1]), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
+              for (int i = 0; i < 8; ++i) {
+                float v0 = __uint_as_float(x[2 * i]), v1 = __uint_as_float(x[2 * i + 1]);
+                if (x_add) { v0 += __uint_as_float(x_add[2 * i]); v1 += __uint_as_float(x_add[2 * i + 1]); }
+                v2[i] = f2::fma(f2::pk(v0, v1), sc2, f2::pk(b[2 * i], b[2 * i + 1]));
+              }
             }
             if (gn) {
               float ga[16], be[16], te[16];
@@ -403,14 +464,14 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
                 v2[i] = f2::mish_add(t, f2::pk(te[2 * i], te[2 * i + 1]));
               }
             }
-            if (!valid) continue;
+            if (!valid) return;
             if (res) {
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
-                float x[8];
-                tc_chunk_sum<EL>(rh[m], rl[m], a.res.lo != nullptr, x);
+                float xr[8];
+                tc_chunk_sum<EL>(rh[m], rl[m], a.res.lo != nullptr, xr);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v2[m * 4 + e] = f2::add(v2[m * 4 + e], f2::pk(x[2 * e], x[2 * e + 1]));
+                for (int e = 0; e < 4; ++e) v2[m * 4 + e] = f2::add(v2[m * 4 + e], f2::pk(xr[2 * e], xr[2 * e + 1]));
               }
             }
             if (o_hi || (!is_aux && a.tc_hi)) {
@@ -447,6 +508,40 @@ __global__ void __launch_bounds__(kPm2Threads, 1) conv_pm2_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                   fin2[j] = f2::fma(f2::pk(s_fw[j * COUT + u * 16 + 2 * i], s_fw[j * COUT + u * 16 + 2 * i + 1]), v2[i], fin2[j]);
+            }
+          };
+          // identity residual (blocks.py:164) of one unit: the loads go out before the accumulator wait that hides their latency
+          auto ld_res = [&](int u, uint4 (&rh)[2], uint4 (&rl)[2]) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              rh[m] = make_uint4(0, 0, 0, 0); rl[m] = make_uint4(0, 0, 0, 0);
+              if (res) {
+                const size_t off = img + pm_act_off(a.lout, lo, row, 2 * u + m);
+                rh[m] = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.hi + off);
+                if (a.res.lo) rl[m] = *reinterpret_cast<const uint4*>((const uint8_t*)a.res.lo + off);
+              }
+            }
+          };
+          uint32_t x0[16], x1[16];
+          if (FB == 2) {
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+              uint4 rh[2], rl[2];
+              ld_unit_pair(g_acc, mt, u, x0, x1);
+              ld_res(u, rh, rl);
+              t2::tmem_ld_wait();
+              final_unit(u, x0, x1, rh, rl);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < UNITS; u += 2) {
+              uint4 rh0[2], rl0[2], rh1[2], rl1[2];
+              ld_unit_pair(g_acc, mt, u, x0, x1);
+              ld_res(u, rh0, rl0);
+              ld_res(u + 1, rh1, rl1);
+              t2::tmem_ld_wait();
+              final_unit(u, x0, nullptr, rh0, rl0);
+              final_unit(u + 1, x1, nullptr, rh1, rl1);
             }
           }
           if (valid && !is_aux && a.eps) {

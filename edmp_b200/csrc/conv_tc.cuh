@@ -33,6 +33,11 @@
 
 namespace edmp {
 
+// Trace-mode ablation (tools/tc_trace.py with EDMP_ABLATE, read only when the dbg buffer is set -- never on the product path):
+// bit 0 = the epilogue only does its barrier handshakes, bit 1 = the MMA warp issues no MMAs (commits only).
+static __device__ int g_edmp_ablate;
+
+
 constexpr int kTcRows = 128;                 // rows per CTA tile (UMMA M)
 constexpr int kTcBlockBytes = kTcRows * 128; // bytes of one tiled operand block (128 rows x 128 B)
 constexpr int kTcMaxLin = 13;

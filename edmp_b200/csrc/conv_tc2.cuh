@@ -106,12 +106,23 @@ struct Tc2RunT {
   int b_stage_stride, b_lo_off, b_real_off, b_total_bytes;   // weight stage geometry (bytes)
   int b_pad, slot_bytes;                   // zero tap slots ([Z][real][Z]... layout) of slot_bytes each
   int mma_warps, split;
+  int lean;                                // 1: lean issue path (one thread, tabulated schedule; mma_warps == 1)
   int rot[NR];
   Tc2Args l[NR];
 };
 typedef Tc2RunT<kT2MaxRun> Tc2Run;
 
 namespace t2 {
+// elect.sync: true in exactly one lane of the converged warp; `leader` = that lane's id in every lane
+__device__ __forceinline__ bool elect_leader(uint32_t& leader) {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync %0|px, 0xffffffff;\n\t"
+      "selp.u32 %1, 1, 0, px;\n\t}"
+      : "=r"(leader), "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -228,6 +239,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   __shared__ uint64_t xg_full[2];   // nsplit > 1: "the partial group statistics of every cluster peer have arrived" (by tile parity)
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_par2[2][5 * 128];        // bias | gamma | beta | temb | bres of a column tile (by tile parity)
+  // lean issue path: a layer's MMA schedule, tabulated once per layer as [phase][first chunk | later chunks][input position]
+  // (three packed words per step: the static shared memory must stay within its 7 KB -- the stage rings fill the rest):
+  //   w = n0 | n1 << 8 | acc0 << 16 | n_runs << 24   window widths (slots) of the (at most two) MMA groups of the step, the
+  //                                                  accumulate flag of group 0's first 32-byte K step, 0 runs = position unused
+  //   d = d0 | d1 << 16                              accumulator column offsets;   b = b0 | b1 << 16: weight offsets in 128-byte rows
+  __shared__ uint32_t s_st_w[2][2][kTcMaxLin], s_st_d[2][2][kTcMaxLin], s_st_b[2][2][kTcMaxLin];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? t2::cluster_ctarank() : 0u;
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   auto layer_tiles = [&](int li) { return (r.l[LX(li)].n_row_tiles / CG) * r.l[LX(li)].n_col_tiles; };
 
   long long* dbg = r.l[0].dbg ? r.l[0].dbg + (size_t)blockIdx.x * 16 : nullptr;
+  const int ablate = dbg ? g_edmp_ablate : 0;   // trace-mode ablation (conv_pm.cuh)
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   pdl_launch_dependents();
 
@@ -411,8 +429,155 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           }
         }
       }
+    } else if (r.lean) {
+      // ===== lean MMA issuer (EDMP_MMA_LEAN=1, a tested variant): ONE thread of warp 1 runs the whole issue walk of a layer.
+      // Ablation traces (EDMP_ABLATE=2, profiles/r2_s2_ablation_*.txt) showed the warp-uniform walk below costing 500-700
+      // cycles per step (one activation block = 12 MMAs) with NO MMA issued -- ~250 dynamic instructions of schedule decoding,
+      // descriptor arithmetic, elect / reconvergence and token passing per step.  Here the per-step schedule (window widths,
+      // accumulator / weight offsets, accumulate flags of the first K chunk) is tabulated in shared memory once per layer by the
+      // whole warp, and the elected thread only waits for stages, reads a table entry and issues.  Measured: one lean thread
+      // equals the two alternating warps (1020 rows: 860 against 960 cycles per step in the K loop, the forward within 1-2 %
+      // either way): what remains per step is the shared-memory operand fetch of the MMAs themselves (N = 80: 52 cycles each). =====
+      if (mw == 0) {
+      const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
+      const uint64_t desc0 = umma::make_desc_sw128(0);     // weight tiles: SWIZZLE_128B rows
+      const uint64_t desc_a0 = tc_act_desc0();             // activation blocks: chunk-major, no swizzle (conv_tc.cuh)
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, buf = 0, ne0 = 0, ne1 = 0;
+      for (int li = 0; li < r.n; ++li) {
+        const Tc2Args& a = r.l[LX(li)];
+        const int n_tiles = layer_tiles(li);
+        const int ctl = a.ct / CG;                   // weight rows per slot staged by this CTA
+        // ---- this layer's step table (all lanes) ----
+        __syncwarp();
+        for (int e = lane; e < a.n_phases * 2 * kTcMaxLin; e += 32) {
+          const int li2 = e % kTcMaxLin, v = (e / kTcMaxLin) & 1, p = e / (2 * kTcMaxLin);
+          const Tc2Phase& ph = a.ph[p];
+          uint32_t w = 0, dd = 0, bb = 0;
+          if (li2 < ph.lin && ph.sched[li2].n_slots > 0) {
+            const Tc2Sched sc = ph.sched[li2];
+            // first K chunk: the leading n_acc positions of the window already hold a partial sum, the rest are written
+            // for the first time -> two groups with their own accumulate flag; afterwards one group over the window
+            const int n_first = v == 0 ? sc.n_acc : sc.n_slots;
+            int nr = 0;
+            for (int run = 0; run < 2; ++run) {
+              const int sl0 = run == 0 ? 0 : n_first;
+              const int n = run == 0 ? n_first : sc.n_slots - n_first;
+              if (n <= 0) continue;
+              const uint32_t d = (uint32_t)(ph.d_col + (sc.lo_begin + sl0) * ph.col_step);
+              const uint32_t bo = (uint32_t)((sc.slot_begin + sl0) * ctl);   // 128-byte weight rows
+              if (nr == 0) { w |= (uint32_t)n | ((run == 0 ? 1u : 0u) << 16); dd |= d; bb |= bo; }
+              else { w |= (uint32_t)n << 8; dd |= d << 16; bb |= bo << 16; }
+              ++nr;
+            }
+            w |= (uint32_t)nr << 24;
+          }
+          s_st_w[p][v][li2] = w; s_st_d[p][v][li2] = dd; s_st_b[p][v][li2] = bb;
+        }
+        __syncwarp();
+        uint32_t leader;
+        if (t2::elect_leader(leader)) {
+          long long w_acc = 0, w_a = 0, w_b = 0;
+          const long long t_begin = dbg ? clock64() : 0;
+          if (dbg && li == 0) dbg[2] = dbg[3] = dbg[4] = dbg[5] = 0;
+          const uint32_t idesc_n0 = umma::make_idesc(E::kFmt, kTcRows * CG, 0), ct8 = (uint32_t)a.ct >> 3;
+          auto issue_group = [&](uint32_t idesc, uint32_t d, uint32_t b_off, uint32_t accf, uint64_t da_hi, uint64_t da_lo) {
+            const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
+            const uint64_t db_lo = desc0 | (uint64_t)(((b_off + (uint32_t)b_lo_off) & 0x3FFFF) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
+              const uint32_t acc = accf | (uint32_t)(ks > 0);
+              if (CG == 2) {
+                if (r.split) {
+                  t2::mma_f16_cg2(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                  t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                  t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
+                } else {
+                  t2::mma_f16_cg2(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                }
+              } else {
+                if (r.split) {
+                  umma::mma_bf16(d, da_lo + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                  umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_lo + 2 * ks, idesc, 1u);
+                  umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, 1u);
+                } else {
+                  umma::mma_bf16(d, da_hi + kTcActKStep * ks, db_hi + 2 * ks, idesc, acc);
+                }
+              }
+            }
+          };
+          for (int t = first_tile(li); t < n_tiles; t += n_walkers) {
+            uint32_t ab;                               // accumulator buffer of this tile
+            {
+              const long long tw = dbg ? clock64() : 0;
+              if (a.acc_bufs == 2) {
+                ab = buf;
+                t2::wait(acc_empty + ab, ((ab ? ne1 : ne0) & 1u) ^ 1u);
+                if (ab) ++ne1; else ++ne0;
+                buf ^= 1;
+              } else {
+                t2::wait(acc_empty + 0, (ne0 & 1u) ^ 1u);
+                t2::wait(acc_empty + 1, (ne1 & 1u) ^ 1u);
+                ++ne0; ++ne1;
+                ab = 0; buf = 0;
+              }
+              if (dbg) w_acc += clock64() - tw;
+            }
+            umma::tc_fence_after();
+            const uint32_t acc0 = tmem_base + ab * (uint32_t)a.acc_stride;
+            for (int p = 0; p < a.n_phases; ++p) {
+              const Tc2Phase& ph = a.ph[p];
+              const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+              const int ph_lin = ph.lin;
+              for (int cc = 0; cc < kc; ++cc) {
+                {
+                  const long long tw = dbg ? clock64() : 0;
+                  t2::wait(b_full + bs, bph);
+                  if (CG == 2) t2::wait(pb_full + bs, bph);
+                  if (dbg) w_b += clock64() - tw;
+                }
+                const uint32_t b_base = b0 + bs * (uint32_t)b_stage_stride;
+                const int v = cc == 0 ? 0 : 1;
+                for (int li2 = 0; li2 < ph_lin; ++li2) {
+                  const uint32_t w = s_st_w[p][v][li2], dd = s_st_d[p][v][li2], bb = s_st_b[p][v][li2];
+                  if ((w >> 24) == 0) continue;        // position unused by this layer
+                  {
+                    const long long tw = dbg ? clock64() : 0;
+                    t2::wait(a_full + as, aph);
+                    if (CG == 2) t2::wait(pa_full + as, aph);
+                    if (dbg) w_a += clock64() - tw;
+                  }
+                  if (!(ablate & 2)) {
+                    const uint32_t a_base = a0 + as * (uint32_t)a_stage_bytes;
+                    const uint64_t da_hi = desc_a0 | (uint64_t)((a_base & 0x3FFFF) >> 4);
+                    const uint64_t da_lo = desc_a0 | (uint64_t)(((a_base + kTcBlockBytes) & 0x3FFFF) >> 4);
+                    // instruction descriptor: N = window x ct (n_dim field = N >> 3 at bit 17)
+                    issue_group(idesc_n0 + (((w & 0xFFu) * ct8) << 17), acc0 + (dd & 0xFFFFu), b_base + ((bb & 0xFFFFu) << 7),
+                                (w >> 16) & 1u, da_hi, da_lo);
+                    if ((w >> 24) == 2)
+                      issue_group(idesc_n0 + ((((w >> 8) & 0xFFu) * ct8) << 17), acc0 + (dd >> 16), b_base + ((bb >> 16) << 7), 0u, da_hi, da_lo);
+                  }
+                  // frees the A stage (in both CTAs of a pair) once these MMAs have read it
+                  if (CG == 2) t2::commit_cg2(a_empty + as); else umma::mma_commit(a_empty + as);
+                  if (++as == (uint32_t)r.a_stages) { as = 0; aph ^= 1; }
+                }
+                // ... and the weight stage after the chunk / the accumulator after the tile
+                if (CG == 2) t2::commit_cg2(b_empty + bs); else umma::mma_commit(b_empty + bs);
+                if (p == a.n_phases - 1 && cc == kc - 1) { if (CG == 2) t2::commit_cg2(acc_full + ab); else umma::mma_commit(acc_full + ab); }
+                if (++bs == (uint32_t)r.b_stages) { bs = 0; bph ^= 1; }
+              }
+            }
+          }
+          if (dbg) { dbg[2] += w_acc; dbg[3] += w_b; dbg[4] += w_a; dbg[5] += clock64() - t_begin; }
+        }
+        __syncwarp();
+        // the ring / accumulator state lives in the elected thread: hand it to every lane for the next layer's election
+        as = __shfl_sync(0xffffffffu, as, leader); aph = __shfl_sync(0xffffffffu, aph, leader);
+        bs = __shfl_sync(0xffffffffu, bs, leader); bph = __shfl_sync(0xffffffffu, bph, leader);
+        buf = __shfl_sync(0xffffffffu, buf, leader); ne0 = __shfl_sync(0xffffffffu, ne0, leader); ne1 = __shfl_sync(0xffffffffu, ne1, leader);
+      }
+      }
     } else if (mw < nw) {
-      // ===== MMA issuer: warp-uniform walk, one elected lane issues.  With two issuing warps the steps (one
+      // ===== MMA issuer (default): warp-uniform walk, one elected lane issues.  With two issuing warps the steps (one
       // activation block = 12 MMAs) alternate between them: while one warp sits in its (blocking) MMA issue the
       // other already waits for the next stage and builds its descriptors, so that per-step overhead leaves the
       // tensor pipe's critical path (profiles/micro/r1_mma_pipe.txt).  A token (named barrier + tcgen05 fences)
@@ -492,7 +657,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
                   const uint64_t db_hi = desc0 | (uint64_t)((b_off & 0x3FFFF) >> 4);
                   const uint64_t db_lo = desc0 | (uint64_t)(((b_off + b_lo_off) & 0x3FFFF) >> 4);
                   const uint32_t accf = run == 0 ? 1u : 0u;
-                  if (umma::elect_one()) {
+                  if (!(ablate & 2) && umma::elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {   // 32-byte K steps inside the 128-byte swizzle atom
                       const uint32_t acc = accf | (uint32_t)(ks > 0);
@@ -612,6 +777,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           c0 = col & (ct - 1);
         }
       };
+      long long tf0 = 0;
+      if (!(ablate & 1)) {
       if (a.mode != TC_BIAS) {
         // GroupNorm(8) over (cg channels x L positions) of this row (blocks.py:24-26).  Every 16-column unit (8-column
         // meet in shared memory among the four warps of this lane quarter and are combined with
@@ -749,7 +916,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         t2::bar_quarter(quarter);
         if (dbg) t_bar += clock64() - tb0;
       }
-      const long long tf0 = dbg ? clock64() : 0;
+      tf0 = dbg ? clock64() : 0;
 
       // ---- normalise, Mish, time embedding, residual, hi/lo split, store.  Every load of a batch (accumulator,
       // residual accumulator, identity-residual operand blocks) is issued first; the group statistics are combined
@@ -875,6 +1042,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
           }
         }
       }
+      }   // !(ablate & 1)
       {
         // every accumulator read of this tile is complete: hand the TMEM buffer back to the MMA warp
         umma::tc_fence_before();

@@ -209,6 +209,7 @@ struct Layer {
   int cta_group = 1;            // LAYER_TC2: 2 = CTA pairs (cta_group::2)
   int b_pad = 0;                // LAYER_TC2 pairs: weight stages with shared resident zero slots
   int nsplit = 1;               // LAYER_TC2: CTAs of a cluster that share one GroupNorm group (column split, small batches)
+  int t2_lean = 0;              // LAYER_TC2: lean issue path (EDMP_MMA_LEAN=1 at creation; implies one issuing warp)
   int t2_max_slots = 0;         // LAYER_TC2: weight slots per stage, bytes per slot, bytes of the GroupNorm piece area
   size_t t2_slot_bytes = 0, t2_part_bytes = 0;
   size_t tc_smem = 0;
@@ -676,8 +677,12 @@ struct Builder {
         all = all && t.ph[p].lin >= 2;
         for (int li = 0; li < t.ph[p].lin; ++li) all = all && t.ph[p].sched[li].n_slots > 0;
       }
+      // (EDMP_MMA_LEAN=1: the lean issue path -- one thread, tabulated schedule, conv_tc2.cuh -- a tested variant: it matches
+      // the two alternating warps within 1-2 % at both batch sizes, profiles/r2_s2_experiments.md)
+      const bool lean = getenv("EDMP_MMA_LEAN") != nullptr && atoi(getenv("EDMP_MMA_LEAN")) != 0;
       static const int want = getenv("EDMP_MMA_WARPS") ? atoi(getenv("EDMP_MMA_WARPS")) : 2;
-      v.mma_warps = (all && want == 2) ? 2 : 1;
+      v.mma_warps = (!lean && all && want == 2) ? 2 : 1;
+      ly.t2_lean = lean ? 1 : 0;
     }
     // bytes of n weight stages (padded layout: per part n * (max_slots + 1) + 1 slots, see conv_tc2.cuh)
     auto b_bytes = [&](int n) {
@@ -690,7 +695,9 @@ struct Builder {
     const size_t part_bytes = ((size_t)(cols / 16) * (t.cg == 8 ? 2 : 1) + n_groups) * 1024 + (ly.nsplit > 1 ? 8192 : 0);
     const size_t budget = 232448 - 1024 - 7168 - part_bytes;   // dynamic limit - alignment slack - static shared memory - pieces
     v.b_stages = (b_bytes(3) + 3 * a_stage <= budget) ? 3 : ((b_bytes(2) + 2 * a_stage <= budget) ? 2 : 1);
+    if (getenv("EDMP_MAX_B_STAGES")) v.b_stages = std::min(v.b_stages, std::max(1, atoi(getenv("EDMP_MAX_B_STAGES"))));
     v.a_stages = (int)std::min<size_t>(kT2MaxAStages, (budget - b_bytes(v.b_stages)) / a_stage);
+    if (getenv("EDMP_MAX_A_STAGES")) v.a_stages = std::min(v.a_stages, std::max(2, atoi(getenv("EDMP_MAX_A_STAGES"))));
     ok = ok && v.a_stages >= 2;
     ly.kind = LAYER_TC2;
     ly.tc_smem = 1024 + v.a_stages * a_stage + b_bytes(v.b_stages) + part_bytes;
@@ -1399,11 +1406,14 @@ static bool plan_run(const UNet* u, int first, int n, UNet::Launch* out) {
     return l0.b_pad ? (size_t)nparts * ((size_t)k * (max_slots + 1) + 1) * slot_bytes : (size_t)k * part_bytes * nparts;
   };
   const size_t budget = 232448 - 1024 - 7168 - part_max;   // dynamic limit - alignment slack - static shared memory - pieces
+  // (EDMP_MAX_B_STAGES / EDMP_MAX_A_STAGES: A/B knobs for the operand-feed experiments, profiles/r2_stage_sweep.txt)
+  const int cap_b = getenv("EDMP_MAX_B_STAGES") ? std::max(1, atoi(getenv("EDMP_MAX_B_STAGES"))) : 3;
+  const int cap_a = getenv("EDMP_MAX_A_STAGES") ? std::max(2, atoi(getenv("EDMP_MAX_A_STAGES"))) : kT2MaxAStages;
   int bst = 0;
-  for (int k = 3; k >= 1 && !bst; --k)
+  for (int k = std::min(3, cap_b); k >= 1 && !bst; --k)
     if (b_bytes(k) + (size_t)std::max(2, std::min(k, 3)) * a_stage <= budget) bst = k;
   if (!bst) return false;
-  const int ast = (int)std::min<size_t>(kT2MaxAStages, (budget - b_bytes(bst)) / a_stage);
+  const int ast = (int)std::min<size_t>(std::min(kT2MaxAStages, cap_a), (budget - b_bytes(bst)) / a_stage);
   if (ast < 2) return false;
   out->first = first; out->n = n; out->run = true;
   out->a_stages = ast; out->b_stages = bst;
@@ -1546,6 +1556,7 @@ static void run_tc2(UNet* u, const UNet::Launch& L, const float* temb_row, int r
   r.b_stage_stride = L.b_stage_stride; r.b_lo_off = L.b_lo_off; r.b_real_off = L.b_real_off; r.b_total_bytes = L.b_total_bytes;
   r.b_pad = l0.b_pad; r.slot_bytes = L.slot_bytes;
   r.mma_warps = l0.t2.mma_warps; r.split = u->tc_split ? 1 : 0;
+  r.lean = l0.t2_lean;
   int max_tiles = 0;
   for (int k = 0; k < L.n; ++k) {
     const Layer& ly = u->layers[L.first + k];
@@ -1747,6 +1758,10 @@ int unet_tc_trace(UNet* u, int op, int rows, long long* out_h, int max_ctas, int
   EDMP_CK(cudaMalloc(&d, (size_t)ctas * 16 * sizeof(long long)));
   EDMP_CK(cudaMemsetAsync(d, 0, (size_t)ctas * 16 * sizeof(long long), st));
   u->dbg = d;
+  {
+    const int ablate = getenv("EDMP_ABLATE") ? atoi(getenv("EDMP_ABLATE")) : 0;
+    EDMP_CK(cudaMemcpyToSymbolAsync(g_edmp_ablate, &ablate, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  }
   const float* temb_row = u->temb;
   float* eps_tmp = nullptr;
   if (ly.pm_final) EDMP_CK(cudaMalloc(&eps_tmp, (size_t)rows * kRowElems * sizeof(float)));

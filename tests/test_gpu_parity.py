@@ -115,7 +115,8 @@ def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, monkeypatch):
         assert np.abs(eps - ref).max() <= EPS_TOL[prec]
 
 
-@pytest.mark.parametrize("env", ["EDMP_PM_V1", "EDMP_TC_V1", "EDMP_NO_CHAIN", "EDMP_PM_PAIR", "EDMP_NO_NARROW", "EDMP_UP3_V1"])
+@pytest.mark.parametrize("env", ["EDMP_PM_V1", "EDMP_TC_V1", "EDMP_NO_CHAIN", "EDMP_PM_PAIR", "EDMP_NO_NARROW", "EDMP_UP3_V1",
+                                 "EDMP_MMA_LEAN", "EDMP_NO_PM_FUSEB"])
 def test_unet_fallback_kernel_generations_match_oracle(tmp_path_factory, sd, env, monkeypatch):
     """The first-generation kernels (conv_pm / conv_tc, selected by EDMP_PM_V1 / EDMP_TC_V1) and the un-chained launch order
     read and write the same activation layouts as the default path: they must keep matching the oracle."""
