@@ -34,7 +34,8 @@
 namespace edmp {
 
 // Trace-mode ablation (tools/tc_trace.py with EDMP_ABLATE, read only when the dbg buffer is set -- never on the product path):
-// bit 0 = the epilogue only does its barrier handshakes, bit 1 = the MMA warp issues no MMAs (commits only).
+// bit 0 = the epilogue only does its barrier handshakes, bit 1 = the MMA warp issues no MMAs (commits only),
+// bit 2 = conv_tc2's producer copies nothing (every stage is "full" at once: MMAs on stale shared memory).
 static __device__ int g_edmp_ablate;
 
 

@@ -37,7 +37,7 @@ for i in range(n_ops - 1):
     total = t[:, 7] - t[:, 0]
     span = (t[:, 7].max() - t[:, 0].min())
     raw = buf[:n.value].astype(np.float64)
-    if raw[:, 5].mean() > 0 and raw[:, 8].mean() > 0:   # persistent kernel (conv_tc2): counters instead of stamps
+    if 0 < raw[:, 5].mean() < raw[:, 0].mean():   # persistent kernels (conv_tc2 / conv_pm2): slots 2..6, 8.. are cycle counters, not clock stamps
         lead = raw[raw[:, 5] > 0]   # CTAs whose MMA warp issued (pair leaders / all CTAs of single-CTA layers)
         r = raw.mean(axis=0)
         r[2:6] = lead[:, 2:6].mean(axis=0)
