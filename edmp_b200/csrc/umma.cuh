@@ -25,22 +25,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (suspend-time hint: a waiting thread sleeps in hardware until the phase completes or kMbarSuspendNs pass instead of
+// re-issuing the test every few hundred cycles -- the spin loops of idle roles were ~35 % of conv_pm2's executed
+// instructions and share their scheduler slots with the working epilogue warps; completion still wakes the thread at once)
+constexpr uint32_t kMbarSuspendNs = 10000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU (2^19 x 10 us ~ 5 s).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 19)) {
       printf("edmp: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
