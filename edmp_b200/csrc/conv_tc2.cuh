@@ -169,7 +169,7 @@ __device__ __forceinline__ void wait_cluster(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(umma::smem_u32(bar)), "r"(parity), "r"(umma::kMbarSuspendNs)
         : "memory");
-    if (!ok && ++spins > (1u << 19)) __trap();
+    if (!ok && ++spins > (1u << 22)) __trap();
   }
 }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread, WITHOUT waiting: several loads can be in
@@ -187,7 +187,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!umma::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 19)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 // Mish = x * n / (n + 2), n = e^x (e^x + 2), with the single-instruction ex2 / rcp approximations (relative error

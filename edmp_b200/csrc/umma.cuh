@@ -40,11 +40,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU (2^19 x 10 us ~ 5 s).
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU (2^22 x 10 us ~ 40 s: sanitizer runs are 10-100 x slower than real time).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 19)) {
+    if (++spins > (1u << 22)) {
       printf("edmp: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
