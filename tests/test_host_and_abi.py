@@ -203,10 +203,12 @@ def test_goal_selection_like_the_entry_point():
         scene.select_goal(vol[:2], start, goals)
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    """The bench line committed under profiles/ (written by bench.py on a B200) carries every key of the driver's contract."""
+@pytest.mark.parametrize("line,ref_line", [("r1_final_8190rows_bench.json", "r1_final_reference_arm_bench.json"),
+                                           ("r2_final_8190rows_bench.json", "r2_final_bench_reference.json")])
+def test_committed_bench_line_has_the_contract_keys(line, ref_line):
+    """The bench lines committed under profiles/ (written by bench.py on a B200) carry every key of the driver's contract."""
     import json
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_final_8190rows_bench.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", line)))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -223,7 +225,13 @@ def test_committed_bench_line_has_the_contract_keys():
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0
     assert d["gpu_launches"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r1_final_reference_arm_bench.json")))
+    if line.startswith("r2"):
+        # round 2: strong-scaling block, the Python-API end-to-end numbers, the stock PyTorch-CUDA baseline
+        assert d["strong"]["rows_total"] > 0 and d["e2e_api"]["philox"] > 0 and d["e2e_api"]["numpy"] > 0
+        assert d["gpu_baseline"]["fp32"] > 0 and d["roofline"]["frac"] <= 1.0 / 3.0 + 1e-9   # the x3 modes' cap
+        d8 = json.load(open(os.path.join(ROOT, "profiles", "r2_8gpu_bench.json")))
+        assert d8["n_gpus"] == 8 and d8["metric"] == d["metric"] and d8["strong"]["rows_per_gpu"] * 8 == d8["strong"]["rows_total"]
+    ref = json.load(open(os.path.join(ROOT, "profiles", ref_line)))
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
 
