@@ -34,7 +34,8 @@ namespace edmp {
 constexpr int kT2EpiWarp0 = 3;                       // warp 0: operand producer, 1 (+TMEM) and 2: MMA issue
 constexpr int kT2EpiWarps = 16;
 constexpr int kT2EpiThreads = kT2EpiWarps * 32;
-constexpr int kT2Threads = (kT2EpiWarp0 + kT2EpiWarps) * 32;   // 608
+constexpr int kT2ProdWarp2 = kT2EpiWarp0 + kT2EpiWarps;        // warp 19: the weight-stream producer (EDMP_PRODUCERS != 1)
+constexpr int kT2Threads = (kT2EpiWarp0 + kT2EpiWarps + 1) * 32;   // 640 (registers are granted for 20 warps anyway)
 constexpr int kT2MaxAStages = 4, kT2MaxBStages = 3;
 constexpr int kT2MaxUnits = 16;                      // accumulator columns per tile <= 256
 
@@ -107,6 +108,8 @@ struct Tc2RunT {
   int b_pad, slot_bytes;                   // zero tap slots ([Z][real][Z]... layout) of slot_bytes each
   int mma_warps, split;
   int lean;                                // 1: lean issue path (one thread, tabulated schedule; mma_warps == 1)
+  int producers;                           // operand producer threads: 1 (warp 0: both streams), 2 (+ warp 19: the weight stream), 3 (lean
+                                           // only: + warp 2: the lo parts of the activation stream)
   int rot[NR];
   Tc2Args l[NR];
 };
@@ -308,7 +311,117 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
   if (r.l[0].dep == nullptr) pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-  if (warp == 0) {
+  if (r.producers > 1 && (warp == 0 || warp == kT2ProdWarp2 || (warp == 2 && r.producers == 3))) {
+    // ===== operand producers, one THREAD per stream (default EDMP_PRODUCERS=2; 3: activation lo parts on warp 2 as well).  A thread sustains about one 1-D bulk copy per
+    // 1000 cycles however many stages it keeps in flight, and the rate adds up over issuing threads (tools/micro/l2_feed.cu,
+    // profiles/micro/r2_l2_feed.txt): the six copies of a pair layer's K chunk (2 positions x hi / lo, weights hi / lo) take
+    // one thread ~6k cycles against 3072 of MMA time.  Warp 0: activation blocks (the hi parts only when warp 2 carries the
+    // lo parts: lean issuer), warp 19: weight tiles.  Every thread walks its stream's (layer, tile, phase, chunk[, position])
+    // sequence on its own with blocking waits; the hi thread arms the "stage full" barrier with the byte count of both
+    // parts (a lo copy that lands first only drives the transaction count negative until then). =====
+    if (lane == 0) {
+      if (warp == kT2ProdWarp2) {
+        uint32_t bs = 0, bph = 0;
+        int lb = 0, tb = first_tile(0), ntb = layer_tiles(0), pb = 0, ccb = 0;
+        while (lb < r.n && tb >= ntb) { if (++lb < r.n) { tb = first_tile(lb); ntb = layer_tiles(lb); } }   // layers without a tile for this walker
+        while (lb < r.n) {
+          t2::wait(b_empty + bs, bph ^ 1);
+          const Tc2Args& a = r.l[LX(lb)];
+          const Tc2Phase& ph = a.ph[pb];
+          const int kc = (ph.a.C + ph.b.C) >> E::kShift;
+          const int nt = tb & (a.n_col_tiles - 1);
+          const uint32_t wtile_bytes = (uint32_t)(ph.slots * (a.ct / CG) * 128);
+          const size_t woff = (((size_t)nt * kc + ccb) * CG + rank) * wtile_bytes;
+          uint8_t* dst = b_smem + bs * b_stage_stride + b_real_off;
+          if (ablate & 4) {
+            umma::mbar_arrive(b_full + bs);
+          } else {
+            umma::mbar_arrive_expect_tx(b_full + bs, wtile_bytes * (uint32_t)nparts);
+            umma::bulk_g2s(dst, (const uint8_t*)ph.w_hi + woff, wtile_bytes, b_full + bs);
+            if (r.split) umma::bulk_g2s(dst + b_lo_off, (const uint8_t*)ph.w_lo + woff, wtile_bytes, b_full + bs);
+          }
+          if (++bs == (uint32_t)r.b_stages) { bs = 0; bph ^= 1; }
+          if (++ccb == kc) {
+            ccb = 0;
+            if (++pb == a.n_phases) {
+              pb = 0;
+              tb += n_walkers;
+              while (lb < r.n && tb >= ntb) { if (++lb < r.n) { tb = first_tile(lb); ntb = layer_tiles(lb); } }
+            }
+          }
+        }
+      } else {
+        const bool do_hi = warp == 0, do_lo = r.split && (warp == 2 || r.producers == 2);
+        uint32_t as = 0, aph = 0;
+        int la = 0, ta = first_tile(0), nta = layer_tiles(0), pa = 0, cca = 0, lia = 0;
+        while (la < r.n && ta >= nta) { if (++la < r.n) { ta = first_tile(la); nta = layer_tiles(la); } }
+        if (la < r.n) while (r.l[LX(la)].ph[0].sched[lia].n_slots == 0) ++lia;                                    // leading unused positions
+        if (!do_hi && !do_lo) la = r.n;
+        int ta_ready = -1;                            // (layer, tile) whose row-tile dependency has been observed
+        while (la < r.n) {
+          t2::wait(a_empty + as, aph ^ 1);
+          const Tc2Args& a = r.l[LX(la)];
+          if (a.dep != nullptr && ((la << 20) | ta) != ta_ready) {
+            // first activation load of this tile: the producing layer must have finished this row tile
+            const int rt_dep = (ta >> a.nct_log2) * CG + (int)rank;
+            // (a pair's padding row tile past the batch has no producer: its operand blocks are the zero-filled tail)
+            if (rt_dep * kTcRows < a.rows) {
+              const long long dep_t0 = clock64();
+              while (t2::ld_acquire(a.dep + rt_dep) < a.dep_target) {
+                if (clock64() - dep_t0 > (1ll << 32)) {   // ~2 s: a protocol bug traps instead of hanging the GPU
+                  printf("edmp: conv_tc2 row-tile dependency timed out (block %d, layer %d of the run, row tile %d: %d of %d)\n",
+                         blockIdx.x, la, rt_dep, t2::ld_acquire(a.dep + rt_dep), a.dep_target);
+                  __trap();
+                }
+              }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (bulk copy) reads
+            ta_ready = (la << 20) | ta;
+          }
+          {
+            const Tc2Phase& ph = a.ph[pa];
+            const int ka = ph.a.C >> E::kShift, kb = ph.b.C >> E::kShift;
+            const bool first = cca < ka;
+            const TcOperand& op = first ? ph.a : ph.b;
+            const int c2 = first ? cca : cca - ka;
+            const int kop = first ? ka : kb;
+            const int rt = (ta >> a.nct_log2) * CG + (int)rank;
+            const size_t blk = ((size_t)rt * (ph.lin * kop) + (size_t)lia * kop + c2) * kTcBlockBytes;
+            uint8_t* dst = a_smem + as * a_stage_bytes;
+            if (ablate & 4) {
+              if (do_hi) umma::mbar_arrive(a_full + as);
+            } else {
+              if (do_hi) {
+                umma::mbar_arrive_expect_tx(a_full + as, (uint32_t)a_stage_bytes);
+                umma::bulk_g2s(dst, (const uint8_t*)op.hi + blk, kTcBlockBytes, a_full + as);
+              }
+              if (do_lo) umma::bulk_g2s(dst + kTcBlockBytes, (const uint8_t*)op.lo + blk, kTcBlockBytes, a_full + as);
+            }
+            if (++as == (uint32_t)r.a_stages) { as = 0; aph ^= 1; }
+          }
+          // advance (layer, tile, phase, chunk, position), skipping unused positions and layers without a tile
+          for (;;) {
+            const Tc2Args& c = r.l[LX(la)];
+            const Tc2Phase& cp = c.ph[pa];
+            if (++lia == cp.lin) {
+              lia = 0;
+              if (++cca == ((cp.a.C + cp.b.C) >> E::kShift)) {
+                cca = 0;
+                if (++pa == c.n_phases) {
+                  pa = 0;
+                  ta += n_walkers;
+                  while (la < r.n && ta >= nta) { if (++la < r.n) { ta = first_tile(la); nta = layer_tiles(la); } }
+                }
+              }
+            }
+            if (la >= r.n || r.l[LX(la)].ph[pa].sched[lia].n_slots != 0) break;
+          }
+        }
+      }
+    }
+  } else if (warp == kT2ProdWarp2) {
+    // (one producer thread: this warp has no role)
+  } else if (warp == 0) {
     // (Tried in round 2: FOUR issuing lanes -- activations hi / lo, weights hi / lo.  In isolation a thread sustains only
     // ~19 B/clk of bulk copies however many stages it keeps in flight and the rate adds up over issuing lanes
     // (tools/micro/l2_feed.cu, profiles/micro/r2_l2_feed.txt: 19 / 35 / 62 B/clk/SM for 1 / 2 / 4 lanes) -- but inside this
@@ -443,14 +556,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
         }
       }
     } else if (r.lean) {
-      // ===== lean MMA issuer (EDMP_MMA_LEAN=1, a tested variant): ONE thread of warp 1 runs the whole issue walk of a layer.
+      // ===== lean MMA issuer (default; EDMP_MMA_LEAN=0 selects the first form below): ONE thread of warp 1 runs the whole issue walk of a layer.
       // Ablation traces (EDMP_ABLATE=2, profiles/r2_s2_ablation_*.txt) showed the warp-uniform walk below costing 500-700
       // cycles per step (one activation block = 12 MMAs) with NO MMA issued -- ~250 dynamic instructions of schedule decoding,
       // descriptor arithmetic, elect / reconvergence and token passing per step.  Here the per-step schedule (window widths,
       // accumulator / weight offsets, accumulate flags of the first K chunk) is tabulated in shared memory once per layer by the
       // whole warp, and the elected thread only waits for stages, reads a table entry and issues.  Measured: one lean thread
       // equals the two alternating warps (1020 rows: 860 against 960 cycles per step in the K loop, the forward within 1-2 %
-      // either way): what remains per step is the shared-memory operand fetch of the MMAs themselves (N = 80: 52 cycles each). =====
+      // either way): what remains per step is the shared-memory operand fetch of the MMAs themselves (N = 80: 52 cycles each);
+      // together with the second producer thread it is 1 % (8190 rows) to 3 % (1020 rows) ahead. =====
       if (mw == 0) {
       const uint32_t a0 = umma::smem_u32(a_smem), b0 = umma::smem_u32(b_smem);
       const uint64_t desc0 = umma::make_desc_sw128(0);     // weight tiles: SWIZZLE_128B rows
@@ -590,7 +704,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const __grid_co
       }
       }
     } else if (mw < nw) {
-      // ===== MMA issuer (default): warp-uniform walk, one elected lane issues.  With two issuing warps the steps (one
+      // ===== MMA issuer, first form (EDMP_MMA_LEAN=0): warp-uniform walk, one elected lane issues.  With two issuing warps the steps (one
       // activation block = 12 MMAs) alternate between them: while one warp sits in its (blocking) MMA issue the
       // other already waits for the next stage and builds its descriptors, so that per-step overhead leaves the
       // tensor pipe's critical path (profiles/micro/r1_mma_pipe.txt).  A token (named barrier + tcgen05 fences)

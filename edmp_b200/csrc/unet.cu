@@ -677,9 +677,10 @@ struct Builder {
         all = all && t.ph[p].lin >= 2;
         for (int li = 0; li < t.ph[p].lin; ++li) all = all && t.ph[p].sched[li].n_slots > 0;
       }
-      // (EDMP_MMA_LEAN=1: the lean issue path -- one thread, tabulated schedule, conv_tc2.cuh -- a tested variant: it matches
-      // the two alternating warps within 1-2 % at both batch sizes, profiles/r2_s2_experiments.md)
-      const bool lean = getenv("EDMP_MMA_LEAN") != nullptr && atoi(getenv("EDMP_MMA_LEAN")) != 0;
+      // (default: the lean issue path -- one thread, tabulated schedule, conv_tc2.cuh; EDMP_MMA_LEAN=0: two alternating issuing
+      // warps.  Alone the two forms are within 1-2 % of each other; with the weight stream on its own producer thread
+      // (EDMP_PRODUCERS, run_tc2) the lean form is 1 % ahead at 8190 rows and 3 % at 1020, profiles/r2_s2_experiments.md)
+      const bool lean = getenv("EDMP_MMA_LEAN") == nullptr || atoi(getenv("EDMP_MMA_LEAN")) != 0;
       static const int want = getenv("EDMP_MMA_WARPS") ? atoi(getenv("EDMP_MMA_WARPS")) : 2;
       v.mma_warps = (!lean && all && want == 2) ? 2 : 1;
       ly.t2_lean = lean ? 1 : 0;
@@ -1557,6 +1558,12 @@ static void run_tc2(UNet* u, const UNet::Launch& L, const float* temb_row, int r
   r.b_pad = l0.b_pad; r.slot_bytes = L.slot_bytes;
   r.mma_warps = l0.t2.mma_warps; r.split = u->tc_split ? 1 : 0;
   r.lean = l0.t2_lean;
+  {
+    // operand producer threads (conv_tc2.cuh): 1 = warp 0 issues both streams, 2 = the weight stream moves to warp 19,
+    // 3 = (lean issuer only: warp 2 is free) the lo parts of the activation stream move to warp 2 as well
+    const int want = getenv("EDMP_PRODUCERS") ? std::max(1, std::min(3, atoi(getenv("EDMP_PRODUCERS")))) : 2;
+    r.producers = (want == 3 && !l0.t2_lean) ? 2 : want;
+  }
   int max_tiles = 0;
   for (int k = 0; k < L.n; ++k) {
     const Layer& ly = u->layers[L.first + k];
@@ -1704,7 +1711,7 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
   const int n = nl + (u->final_fused ? 0 : 1);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) EDMP_CK(cudaEventCreate(&e));
-  std::vector<double> acc(n, 0.0);
+  std::vector<std::vector<float>> samples(n);   // per launch: one duration per profiled forward
   const float* temb_row = u->temb + (size_t)(t - 1) * u->temb_width;
   for (int it = 0; it < iters; ++it) {
     if (u->tile_done) EDMP_CK(cudaMemsetAsync(u->tile_done, 0, u->layers.size() * (size_t)u->tile_stride * sizeof(int), st));
@@ -1723,11 +1730,14 @@ int unet_profile(UNet* u, const float* x, int t, int rows, int iters, float* ms,
     for (int i = 0; i < n; ++i) {
       float m = 0.f;
       EDMP_CK(cudaEventElapsedTime(&m, ev[i], ev[i + 1]));
-      acc[i] += m;
+      samples[i].push_back(m);
     }
   }
   for (int i = 0; i < n; ++i) {
-    ms[i] = (float)(acc[i] / iters);
+    // the MEDIAN of the profiled forwards: one forward that catches a clock transition of the power-capped part (seen once:
+    // a 600 us launch read as 837 us in a 10-forward mean) must not move the per-kernel figure
+    std::sort(samples[i].begin(), samples[i].end());
+    ms[i] = (iters & 1) ? samples[i][iters / 2] : 0.5f * (samples[i][iters / 2 - 1] + samples[i][iters / 2]);
     macs[i] = i < nl ? u->launches[i].macs_per_row * rows : (double)kHorizon * u->final_c * kDof * rows;
   }
   for (auto& e : ev) cudaEventDestroy(e);

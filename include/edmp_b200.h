@@ -89,7 +89,7 @@ int edmp_unet_forward(edmp_unet* u, const float* x_d, int t, int rows, float* ep
 int edmp_unet_read_activation(edmp_unet* u, const char* name, int rows, float* out_d, int* C, int* L,
                               void* stream);
 /* measurement: per-kernel device time of one forward (CUDA events on `stream` around every launch,
- * averaged over iters forwards) and the non-padding multiply-accumulates each kernel performs.
+ * the median over iters forwards) and the non-padding multiply-accumulates each kernel performs.
  * ms_h / macs_h hold edmp_unet_launches_per_forward() entries; edmp_unet_op_name(u, i) names op i
  * after the reference module it implements. */
 int edmp_unet_profile(edmp_unet* u, const float* x_d, int t, int rows, int iters, float* ms_h,

@@ -116,13 +116,15 @@ def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, monkeypatch):
 
 
 @pytest.mark.parametrize("env", ["EDMP_PM_V1", "EDMP_TC_V1", "EDMP_NO_CHAIN", "EDMP_PM_PAIR", "EDMP_NO_NARROW", "EDMP_UP3_V1",
-                                 "EDMP_MMA_LEAN", "EDMP_NO_PM_FUSEB"])
+                                 "EDMP_MMA_LEAN=0", "EDMP_NO_PM_FUSEB", "EDMP_PRODUCERS=1", "EDMP_PRODUCERS=3",
+                                 "EDMP_MMA_LEAN=0 EDMP_PRODUCERS=1"])
 def test_unet_fallback_kernel_generations_match_oracle(tmp_path_factory, sd, env, monkeypatch):
     """The first-generation kernels (conv_pm / conv_tc, selected by EDMP_PM_V1 / EDMP_TC_V1) and the un-chained launch order
     read and write the same activation layouts as the default path: they must keep matching the oracle."""
     if "f16x3" not in PRECISIONS:
         pytest.skip("f16x3 not selected")
-    monkeypatch.setenv(env, "1")
+    for kv in env.split():
+        monkeypatch.setenv(*(kv.split("=") if "=" in kv else (kv, "1")))
     m = _model(tmp_path_factory, sd, "f16x3")
     x = torch.randn(137, 7, 50, generator=torch.Generator().manual_seed(5)) * 1.5
     with torch.no_grad():
