@@ -101,11 +101,14 @@ def test_unet_rows_independent_at_full_batch(model):
     assert torch.equal(dup, dup[:1].expand_as(dup))
 
 
-@pytest.mark.parametrize("rows", [130, 300])
-def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, monkeypatch):
+@pytest.mark.parametrize("rows,env", [(130, ""), (300, ""), (300, "EDMP_MMA_LEAN=0 EDMP_PRODUCERS=1"), (300, "EDMP_PRODUCERS=3")])
+def test_unet_cta_pairs_match_oracle(tmp_path_factory, sd, rows, env, monkeypatch):
     """The cta_group::2 path of the horizon 2 / 4 levels (normally chosen for batches >= 4096 rows), forced at a
-    size the oracle finishes in seconds; 300 rows = three row tiles, i.e. a pair with a padding tile."""
+    size the oracle finishes in seconds; 300 rows = three row tiles, i.e. a pair with a padding tile.  Also with the first
+    form of the issuer / producer (two alternating issuing warps, one producer thread) and with three producer threads."""
     monkeypatch.setenv("EDMP_CG2", "1")
+    for kv in env.split():
+        monkeypatch.setenv(*kv.split("="))
     for prec in [p for p in PRECISIONS if p in ("f16x3", "bf16x3")]:
         m = _model(tmp_path_factory, sd, prec)
         x = torch.randn(rows, 7, 50, generator=torch.Generator().manual_seed(rows)) * 1.5

@@ -7,4 +7,4 @@ for R in $ROWS; do
     EDMP_ABLATE=$A timeout 300 python tools/tc_trace.py $R f16x3 > gpurun_out/${TAG}_${R}_a${A}.txt 2>&1
   done
 done
-tail -3 gpurun_out/${TAG}_*_a1.txt
+for f in gpurun_out/${TAG}_*_a1.txt; do tail -n 3 $f; done
